@@ -1,0 +1,221 @@
+/* naruto_b200 -- C-ABI of the B200-native mapping hot path (libnaruto_b200.so).
+ *
+ * Drop-in boundary for NARUTO's neural-implicit mapping iteration.  Every pointer marked "dev" is a
+ * device pointer owned by the caller (in the reference's process: torch CUDA tensors, contiguous, fp32);
+ * the library never allocates, frees or synchronises on the data path; every launch goes to the
+ * cudaStream_t passed as `stream` (an opaque void* here so that the header needs no CUDA include).
+ * All entry points return 0 on success or a negative NrtStatus; nrt_last_error() gives the text.
+ *
+ * Which reference interface each entry point replaces (paths relative to the NARUTO tree,
+ * tp/ = third_parties/coslam/):
+ *
+ *   nrt_plan_create           tp/model/scene_rep.py:18-47 (get_resolution/get_encoding) +
+ *                             tp/model/encodings.py:31-46,61-71 (tcnn.Encoding ctor arguments) +
+ *                             src/slam/coslam/model/scene_rep.py:49-56 (get_uncert_grid dims)
+ *   nrt_encode_fwd/_bwd       tcnn.Encoding HashGrid __call__ / autograd backward, reached from
+ *                             src/slam/coslam/model/scene_rep.py:59,110 and tp/coslam.py:262 (smoothness)
+ *   nrt_oneblob_fwd           tcnn.Encoding OneBlob __call__ (src/slam/coslam/model/scene_rep.py:118,144)
+ *   nrt_decode_fwd            JointEncodingNaruto.query_sdf / query_color_sdf
+ *                             (src/slam/coslam/model/scene_rep.py:98-148; decoder.py:29-41,99-116)
+ *   nrt_sample_z              render_rays depth sampling (src/slam/coslam/model/scene_rep.py:158-180)
+ *   nrt_render_fwd            JointEncodingNaruto.render_rays + raw2outputs + sdf2weights
+ *                             (src/slam/coslam/model/scene_rep.py:150-225,66-96; tp/model/scene_rep.py:64-84)
+ *   nrt_loss_fwd              JointEncodingNaruto.forward train branch + get_sdf_loss/get_masks
+ *                             (src/slam/coslam/model/scene_rep.py:244-287; tp/model/utils.py:81-148)
+ *   nrt_render_bwd            what autograd does for loss.backward() at src/slam/coslam/coslam.py:216,368
+ *                             through the modules above
+ *   nrt_smooth_fwd_bwd        CoSLAM.smoothness + its backward (tp/coslam.py:245-269)
+ *   nrt_adam_step             torch.optim.Adam as configured at src/slam/coslam/coslam.py:409-419,240-243
+ */
+#ifndef NARUTO_B200_H
+#define NARUTO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRT_ABI_VERSION 1
+
+typedef enum NrtStatus {
+  NRT_OK = 0,
+  NRT_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+  NRT_ERR_CUDA = -2,         /* a CUDA runtime call or kernel launch failed */
+  NRT_ERR_NO_DEVICE = -3     /* no CUDA device / wrong architecture (needs sm_100) */
+} NrtStatus;
+
+/* The numbers JointEncodingNaruto reads out of the nested config dict, frozen at construction. */
+typedef struct NrtConfig {
+  int32_t abi_version;        /* = NRT_ABI_VERSION */
+  /* tcnn HashGrid (tp/model/encodings.py:34-45) */
+  int32_t n_levels;           /* 16 */
+  int32_t n_features;         /* 2 */
+  int32_t log2_hashmap_size;  /* config grid.hash_size */
+  int32_t base_resolution;    /* 16 */
+  double per_level_scale;     /* exp2(log2(resolution_sdf/16)/15) */
+  /* tcnn OneBlob */
+  int32_t n_bins;             /* 16 */
+  /* decoder (src/slam/coslam/model/decoder.py) */
+  int32_t hidden_dim;         /* 32 */
+  int32_t geo_feat_dim;       /* 15 */
+  int32_t hidden_dim_color;   /* 32 */
+  /* scene */
+  float bound_min[3];         /* bounding_box[:,0] as float32 */
+  float bound_max[3];         /* bounding_box[:,1] as float32 */
+  int32_t uncert_dims[3];     /* uncert_grid.shape = [Nx,Ny,Nz] */
+  /* sampling / compositing */
+  float trunc;                /* training.trunc */
+  float sc_factor;            /* data.sc_factor */
+  float near_z, far_z;        /* cam.near / cam.far */
+  float depth_trunc;          /* cam.depth_trunc */
+  int32_t n_samples_d;        /* training.n_samples_d */
+  int32_t n_range_d;          /* training.n_range_d */
+  float range_d;              /* training.range_d */
+} NrtConfig;
+
+typedef struct NrtPlan NrtPlan;   /* opaque */
+
+/* Trainable tensors, in the reference's layouts (state_dict keys in comments). */
+typedef struct NrtParams {
+  const float* grid;     /* dev  embed_fn.params                    [n_entries*2] level-major, entry-major, feature-minor */
+  const float* w1;       /* dev  decoder.sdf_net.model.0.weight     [32,80] row-major (out,in) */
+  const float* w2;       /* dev  decoder.sdf_net.model.2.weight     [16,32] */
+  const float* w3;       /* dev  decoder.color_net.model.0.weight   [32,63] */
+  const float* w4;       /* dev  decoder.color_net.model.2.weight   [3,32]  */
+  const float* uncert;   /* dev  uncert_grid                        [Nx,Ny,Nz] */
+} NrtParams;
+
+/* Gradient accumulators, same shapes; every backward entry point ADDS into them (torch .grad semantics). */
+typedef struct NrtGrads {
+  float* grid;
+  float* w1;
+  float* w2;
+  float* w3;
+  float* w4;
+  float* uncert;
+} NrtGrads;
+
+/* Per-ray outputs of render_rays.  Any pointer may be NULL (not materialised). */
+typedef struct NrtRenderOut {
+  float* rgb;         /* dev [B,3] */
+  float* depth;       /* dev [B]   */
+  float* depth_var;   /* dev [B]   */
+  float* acc;         /* dev [B]   acc_map   */
+  float* disp;        /* dev [B]   disp_map  */
+  float* uncert;      /* dev [B]   uncert_map */
+  float* z_vals;      /* dev [B,S] */
+  float* raw;         /* dev [B,S,5] = rgb logits(3), sdf, raw uncertainty */
+  float* weights;     /* dev [B,S] */
+  float* feat;        /* dev [B*S,32] hash features, saved for nrt_render_bwd (training) */
+} NrtRenderOut;
+
+#define NRT_N_LOSS 8
+/* losses[] layout written by nrt_loss_fwd: */
+enum { NRT_LOSS_RGB = 0, NRT_LOSS_DEPTH = 1, NRT_LOSS_SDF = 2, NRT_LOSS_FS = 3, NRT_LOSS_UNCERT = 4,
+       NRT_LOSS_PSNR = 5, NRT_LOSS_UNCERT_MIN = 6 /* min over rays of uncert_map (the reference asserts > 0) */,
+       NRT_LOSS_RESERVED = 7 };
+
+#define NRT_N_STATS 16
+/* stats[] (device, fp64) layout shared by nrt_loss_fwd / nrt_render_bwd; a multi-GPU caller sums the
+ * first NRT_N_STATS_SUM entries across ranks (nrt_loss_partial -> all-reduce -> nrt_loss_finalize). */
+enum { NRT_STAT_N_RAYS = 0, NRT_STAT_N_VALID = 1, NRT_STAT_N_FS = 2, NRT_STAT_N_SDF = 3, NRT_STAT_N_SAMPLES = 4,
+       NRT_STAT_RGB_SQ = 5, NRT_STAT_DEPTH_SQ = 6, NRT_STAT_FS_SQ = 7, NRT_STAT_SDF_SQ = 8,
+       NRT_STAT_INV2U = 9, NRT_STAT_LOGU = 10, NRT_N_STATS_SUM = 11, NRT_STAT_UNCERT_MIN = 11 };
+
+const char* nrt_last_error(void);
+int nrt_abi_version(void);
+
+/* ---- plan ------------------------------------------------------------------------------------ */
+int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out);
+void nrt_plan_destroy(NrtPlan* plan);
+/* sizes derived from the config: n_grid_floats = sum(level sizes)*n_features, n_samples = n_samples_d+n_range_d */
+int nrt_plan_sizes(const NrtPlan* plan, int64_t* n_grid_floats, int32_t* n_samples, int32_t* n_enc_dims);
+/* host arrays of length n_levels: the level table (tcnn grid_scale/grid_resolution/offset table) */
+int nrt_plan_levels(const NrtPlan* plan, float* scale, int32_t* resolution, int32_t* size, int32_t* offset);
+
+/* ---- encodings (lower seam: tcnn.Encoding) --------------------------------------------------- */
+/* x: dev [n,3] already normalised to the bound; out: dev [n,32] */
+int nrt_encode_fwd(const NrtPlan* plan, const float* grid, const float* x, int64_t n, float* out, void* stream);
+/* dgrid += scatter(dout); dx (dev [n,3], may be NULL) = d out / d x contracted with dout (overwritten) */
+int nrt_encode_bwd(const NrtPlan* plan, const float* grid, const float* x, int64_t n, const float* dout,
+                   float* dgrid, float* dx, void* stream);
+/* out: dev [n,48] */
+int nrt_oneblob_fwd(const NrtPlan* plan, const float* x, int64_t n, float* out, void* stream);
+/* dx: dev [n,3] (overwritten) */
+int nrt_oneblob_bwd(const NrtPlan* plan, const float* x, int64_t n, const float* dout, float* dx, void* stream);
+
+/* ---- point decode (query_sdf / query_color_sdf) ---------------------------------------------- */
+/* x: dev [n,3] normalised.  raw: dev [n,5] or NULL; sdf_uncert: dev [n,2] or NULL; geo: dev [n,15] or NULL.
+ * with_color = 0 skips the colour MLP (query_sdf); raw then requires with_color = 1. */
+int nrt_decode_fwd(const NrtPlan* plan, const NrtParams* params, const float* x, int64_t n, int with_color,
+                   float* raw, float* sdf_uncert, float* geo, void* stream);
+
+/* ---- rays ------------------------------------------------------------------------------------ */
+/* z_vals: dev [B,S].  u: dev [B,S] uniform draws (the reference's torch.rand) or NULL;
+ * when u == NULL and perturb != 0 the kernel draws its own Philox stream from `seed`. */
+int nrt_sample_z(const NrtPlan* plan, const float* target_d, int64_t n_rays, const float* u, int perturb,
+                 uint64_t seed, float* z_vals, void* stream);
+
+/* rays_o, rays_d: dev [B,3]; target_d: dev [B] (may be NULL iff z_in != NULL).
+ * z_in: dev [B,S] externally sampled depths (parity mode) or NULL (sampled in-kernel as nrt_sample_z). */
+int nrt_render_fwd(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
+                   const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb,
+                   uint64_t seed, const NrtRenderOut* out, void* stream);
+
+/* raw2outputs + sdf2weights on caller-provided samples (JointEncodingNaruto.raw2outputs,
+ * src/slam/coslam/model/scene_rep.py:66-96): raw dev [B,n_samples,5], z dev [B,n_samples]; fills the per-ray
+ * fields and `weights` of out. */
+int nrt_composite_fwd(const NrtPlan* plan, const float* raw, const float* z, int64_t n_rays, int32_t n_samples,
+                      const NrtRenderOut* out, void* stream);
+
+/* Loss statistics of one ray shard.  stats: dev fp64 buffer of nrt_loss_stats_bytes() bytes, zero-filled once
+ * by the caller at allocation; its first NRT_N_STATS doubles are overwritten with this shard's sums (the rest
+ * is scratch for the deterministic cross-block reduction). */
+int64_t nrt_loss_stats_bytes(void);
+int nrt_loss_partial(const NrtPlan* plan, const NrtRenderOut* rend, const float* target_rgb, const float* target_d,
+                     int64_t n_rays, double* stats, void* stream);
+/* losses (dev fp32 [NRT_N_LOSS]) from (globally summed) stats. */
+int nrt_loss_finalize(const NrtPlan* plan, const double* stats, float* losses, void* stream);
+/* convenience: partial + finalize for the single-GPU case */
+int nrt_loss_fwd(const NrtPlan* plan, const NrtRenderOut* rend, const float* target_rgb, const float* target_d,
+                 int64_t n_rays, double* stats, float* losses, void* stream);
+
+/* Backward of the point decode alone (autograd of query_color_sdf / run_network): draw: dev [n,5] = dL/d raw.
+ * Adds into grads; workspace: dev scratch of n*32*4 bytes. */
+int nrt_decode_bwd(const NrtPlan* plan, const NrtParams* params, const float* x, int64_t n, const float* draw,
+                   const NrtGrads* grads, void* workspace, void* stream);
+
+/* Backward of total = sum_k loss_grad[k] * losses[k] (k < 5; loss_grad is a dev fp32 [5] array holding
+ * dL/d{rgb,depth,sdf,fs,uncert}_loss, i.e. the reference's loss weights when called from get_loss_from_ret).
+ * rend must hold z_vals, raw, feat and the per-ray rgb/depth/uncert written by nrt_render_fwd.
+ * workspace: dev scratch of nrt_render_bwd_workspace(n_rays) bytes. */
+int64_t nrt_render_bwd_workspace(const NrtPlan* plan, int64_t n_rays);
+int nrt_render_bwd(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
+                   const float* target_rgb, const float* target_d, int64_t n_rays, const NrtRenderOut* rend,
+                   const double* stats, const float* loss_grad, const NrtGrads* grads, void* workspace,
+                   void* stream);
+
+/* ---- smoothness ------------------------------------------------------------------------------ */
+/* TV loss of the hash features on the (n-1)^3 lattice of CoSLAM.smoothness (n = smooth_pts, pitch `voxel`,
+ * border `margin`).  rand6: dev fp32 [6] = the reference's two uniform draws, torch.rand(3) (offset) then
+ * torch.rand((1,1,1,3)) (jitter); kept on the device so a captured CUDA graph can be replayed with fresh draws.
+ * loss (dev fp32 [1], overwritten) = tv / n^3;  dgrid += loss_scale * d loss / d grid (dgrid may be NULL).
+ * workspace: dev scratch of nrt_smooth_workspace(n) bytes. */
+int64_t nrt_smooth_workspace(const NrtPlan* plan, int32_t n);
+int nrt_smooth_fwd_bwd(const NrtPlan* plan, const float* grid, const float* rand6, int32_t n, double voxel,
+                       double margin, float loss_scale, float* loss, float* dgrid, void* workspace, void* stream);
+
+/* ---- optimiser ------------------------------------------------------------------------------- */
+/* torch.optim.Adam (no amsgrad): grad += weight_decay * p; m, v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
+ * step = 1-based step count of this update; if step_dev != NULL the count is read from that device int32
+ * instead (graph replay; advance it with nrt_counter_add).  zero_grad != 0 clears the gradient in the same pass. */
+int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,
+                  const int32_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int zero_grad, void* stream);
+int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NARUTO_B200_H */

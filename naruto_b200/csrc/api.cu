@@ -1,0 +1,269 @@
+// extern "C" entry points of libnaruto_b200.so (see include/naruto_b200.h for the contract).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+// launchers implemented in forward.cu / backward.cu / optim.cu
+int launch_encode_fwd(const NrtPlan*, const float*, const float*, int64_t, float*, cudaStream_t);
+int launch_oneblob_fwd(const float*, int64_t, float*, cudaStream_t);
+int launch_oneblob_bwd(const float*, int64_t, const float*, float*, cudaStream_t);
+int launch_decode_fwd(const NrtPlan*, const NrtParams*, const float*, int64_t, int, float*, float*, float*, cudaStream_t);
+int launch_sample_z(const NrtPlan*, const float*, int64_t, const float*, int, uint64_t, float*, cudaStream_t);
+int launch_render_fwd(const NrtPlan*, const NrtParams*, const float*, const float*, const float*, int64_t, const float*,
+                      const float*, int, uint64_t, const NrtRenderOut*, cudaStream_t);
+int launch_composite_fwd(const NrtPlan*, const float*, const float*, int64_t, int, const NrtRenderOut*, cudaStream_t);
+int64_t loss_stats_doubles();
+int launch_loss_partial(const NrtPlan*, const NrtRenderOut*, const float*, const float*, int64_t, double*, cudaStream_t);
+int launch_loss_finalize(const double*, float*, cudaStream_t);
+int launch_composite_bwd(const NrtPlan*, const NrtRenderOut*, const float*, const float*, int64_t, const double*, const float*,
+                         float*, cudaStream_t);
+int launch_decode_bwd(const NrtPlan*, const NrtParams*, const PointSource&, int64_t, const float*, const float*, float*,
+                      const NrtGrads*, cudaStream_t);
+int launch_encode_bwd(const NrtPlan*, const float*, const PointSource&, int64_t, const float*, float, float*, float*,
+                      cudaStream_t);
+int launch_smooth(const NrtPlan*, const float*, const float*, int, double, double, float, float*, float*, void*, cudaStream_t);
+int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
+                cudaStream_t);
+int launch_counter_add(int*, int, cudaStream_t);
+
+static thread_local char g_err[512] = "";
+
+void nrt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+const char* nrt_last_error(void) { return g_err; }
+int nrt_abi_version(void) { return NRT_ABI_VERSION; }
+
+int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
+  NRT_REQUIRE(cfg && out, "null config/out");
+  NRT_REQUIRE(cfg->abi_version == NRT_ABI_VERSION, "NrtConfig.abi_version mismatch");
+  NRT_REQUIRE(cfg->n_levels == NRT_L && cfg->n_features == 2, "kernels are built for a 16-level x 2-feature hash grid");
+  NRT_REQUIRE(cfg->n_bins == NRT_BINS, "kernels are built for OneBlob n_bins=16");
+  NRT_REQUIRE(cfg->hidden_dim == NRT_H && cfg->hidden_dim_color == NRT_H && cfg->geo_feat_dim == NRT_GEO,
+              "kernels are built for hidden_dim=32, hidden_dim_color=32, geo_feat_dim=15");
+  NRT_REQUIRE(cfg->log2_hashmap_size >= 4 && cfg->log2_hashmap_size <= 28, "log2_hashmap_size out of range");
+  NRT_REQUIRE(cfg->n_samples_d >= 0 && cfg->n_range_d >= 1, "n_samples_d >= 0 and n_range_d >= 1 required");
+  NRT_REQUIRE(cfg->n_samples_d + cfg->n_range_d <= NRT_SMAX, "more than 256 samples per ray");
+  NRT_REQUIRE(cfg->uncert_dims[0] > 0 && cfg->uncert_dims[1] > 0 && cfg->uncert_dims[2] > 0, "uncert_dims");
+  NRT_REQUIRE(cfg->trunc > 0.f, "trunc must be positive");
+  NrtPlan* p = new (std::nothrow) NrtPlan();
+  NRT_REQUIRE(p != nullptr, "out of host memory");
+  p->cfg = *cfg;
+  DevPlan& d = p->dev;
+  // level table: tcnn GridEncoding ctor (offset table) + grid_scale / grid_resolution, evaluated in fp64 and
+  // rounded once to fp32 (the same rule as oracle/tcnn_shim.py so both sides hold identical bits)
+  uint64_t offset = 0;
+  for (int l = 0; l < NRT_L; ++l) {
+    double sc = std::exp2((double)l * std::log2(cfg->per_level_scale)) * (double)cfg->base_resolution - 1.0;
+    float scale = (float)sc;
+    uint32_t res = (uint32_t)std::ceil(scale) + 1u;
+    uint64_t dense = (uint64_t)res * res * res;
+    const uint64_t cap = 0xFFFFFFFFull / 2;
+    if (dense > cap) dense = cap;
+    dense = (dense + 7) / 8 * 8;
+    uint64_t size = dense < (1ull << cfg->log2_hashmap_size) ? dense : (1ull << cfg->log2_hashmap_size);
+    d.lv[l].scale = scale;
+    d.lv[l].res = res;
+    d.lv[l].size = (uint32_t)size;
+    d.lv[l].offset = (uint32_t)offset;
+    d.lv[l].hashed = ((uint64_t)res * res * res > size) ? 1u : 0u;
+    d.lv[l].res2 = res * res;
+    offset += size;
+  }
+  NRT_REQUIRE(offset < (1ull << 31), "hash table too large for 32-bit entry offsets");
+  p->n_grid_floats = (int64_t)offset * 2;
+  for (int i = 0; i < 3; ++i) {
+    d.bb_min[i] = cfg->bound_min[i];
+    d.bb_ext[i] = cfg->bound_max[i] - cfg->bound_min[i];     // fp32 subtraction, as the tensor op
+    d.ud[i] = cfg->uncert_dims[i];
+  }
+  d.trunc = cfg->trunc;
+  d.sc_trunc = (float)((double)cfg->sc_factor * (double)cfg->trunc);
+  d.near_z = cfg->near_z;
+  d.far_z = cfg->far_z;
+  d.depth_trunc = cfg->depth_trunc;
+  d.range_d = cfg->range_d;
+  d.n_d = cfg->n_samples_d;
+  d.n_r = cfg->n_range_d;
+  d.S = cfg->n_samples_d + cfg->n_range_d;
+  p->sm_count = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) p->sm_count = sms;
+  }
+  (void)cudaGetLastError();   // plan creation is legal without a device (CPU-side symbol/level tests)
+  *out = p;
+  return NRT_OK;
+}
+
+void nrt_plan_destroy(NrtPlan* plan) { delete plan; }
+
+int nrt_plan_sizes(const NrtPlan* plan, int64_t* n_grid_floats, int32_t* n_samples, int32_t* n_enc_dims) {
+  NRT_REQUIRE(plan, "null plan");
+  if (n_grid_floats) *n_grid_floats = plan->n_grid_floats;
+  if (n_samples) *n_samples = plan->dev.S;
+  if (n_enc_dims) *n_enc_dims = NRT_ENC;
+  return NRT_OK;
+}
+
+int nrt_plan_levels(const NrtPlan* plan, float* scale, int32_t* resolution, int32_t* size, int32_t* offset) {
+  NRT_REQUIRE(plan, "null plan");
+  for (int l = 0; l < NRT_L; ++l) {
+    if (scale) scale[l] = plan->dev.lv[l].scale;
+    if (resolution) resolution[l] = (int32_t)plan->dev.lv[l].res;
+    if (size) size[l] = (int32_t)plan->dev.lv[l].size;
+    if (offset) offset[l] = (int32_t)plan->dev.lv[l].offset;
+  }
+  return NRT_OK;
+}
+
+int nrt_encode_fwd(const NrtPlan* plan, const float* grid, const float* x, int64_t n, float* out, void* stream) {
+  NRT_REQUIRE(plan && grid && (n == 0 || (x && out)) && n >= 0, "encode_fwd arguments");
+  return launch_encode_fwd(plan, grid, x, n, out, (cudaStream_t)stream);
+}
+
+int nrt_encode_bwd(const NrtPlan* plan, const float* grid, const float* x, int64_t n, const float* dout, float* dgrid,
+                   float* dx, void* stream) {
+  NRT_REQUIRE(plan && grid && n >= 0 && (n == 0 || (x && dout)), "encode_bwd arguments");
+  PointSource src{x, nullptr, nullptr, nullptr, 1};
+  return launch_encode_bwd(plan, grid, src, n, dout, 1.0f, dgrid, dx, (cudaStream_t)stream);
+}
+
+int nrt_oneblob_fwd(const NrtPlan* plan, const float* x, int64_t n, float* out, void* stream) {
+  NRT_REQUIRE(plan && n >= 0 && (n == 0 || (x && out)), "oneblob_fwd arguments");
+  return launch_oneblob_fwd(x, n, out, (cudaStream_t)stream);
+}
+
+int nrt_oneblob_bwd(const NrtPlan* plan, const float* x, int64_t n, const float* dout, float* dx, void* stream) {
+  NRT_REQUIRE(plan && n >= 0 && (n == 0 || (x && dout && dx)), "oneblob_bwd arguments");
+  return launch_oneblob_bwd(x, n, dout, dx, (cudaStream_t)stream);
+}
+
+static int check_params(const NrtParams* p) {
+  NRT_REQUIRE(p && p->grid && p->w1 && p->w2 && p->w3 && p->w4 && p->uncert, "NrtParams has a null tensor");
+  return NRT_OK;
+}
+
+int nrt_decode_fwd(const NrtPlan* plan, const NrtParams* params, const float* x, int64_t n, int with_color, float* raw,
+                   float* sdf_uncert, float* geo, void* stream) {
+  NRT_REQUIRE(plan && n >= 0 && (n == 0 || x), "decode_fwd arguments");
+  if (int rc = check_params(params)) return rc;
+  NRT_REQUIRE(!(raw && !with_color), "raw output needs with_color=1");
+  return launch_decode_fwd(plan, params, x, n, with_color, raw, sdf_uncert, geo, (cudaStream_t)stream);
+}
+
+int nrt_sample_z(const NrtPlan* plan, const float* target_d, int64_t n_rays, const float* u, int perturb, uint64_t seed,
+                 float* z_vals, void* stream) {
+  NRT_REQUIRE(plan && n_rays >= 0 && (n_rays == 0 || (target_d && z_vals)), "sample_z arguments");
+  return launch_sample_z(plan, target_d, n_rays, u, perturb, seed, z_vals, (cudaStream_t)stream);
+}
+
+int nrt_render_fwd(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
+                   const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
+                   const NrtRenderOut* out, void* stream) {
+  NRT_REQUIRE(plan && out && n_rays >= 0 && (n_rays == 0 || (rays_o && rays_d)), "render_fwd arguments");
+  NRT_REQUIRE(z_in || target_d || n_rays == 0, "render_fwd needs target_d or z_in");
+  if (int rc = check_params(params)) return rc;
+  return launch_render_fwd(plan, params, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, (cudaStream_t)stream);
+}
+
+int nrt_composite_fwd(const NrtPlan* plan, const float* raw, const float* z, int64_t n_rays, int32_t n_samples,
+                      const NrtRenderOut* out, void* stream) {
+  NRT_REQUIRE(plan && out && n_rays >= 0 && (n_rays == 0 || (raw && z)), "composite_fwd arguments");
+  NRT_REQUIRE(n_samples >= 1 && n_samples <= NRT_SMAX, "composite_fwd: 1 <= n_samples <= 256");
+  return launch_composite_fwd(plan, raw, z, n_rays, n_samples, out, (cudaStream_t)stream);
+}
+
+int64_t nrt_loss_stats_bytes(void) { return loss_stats_doubles() * (int64_t)sizeof(double); }
+
+int nrt_loss_partial(const NrtPlan* plan, const NrtRenderOut* rend, const float* target_rgb, const float* target_d,
+                     int64_t n_rays, double* stats, void* stream) {
+  NRT_REQUIRE(plan && rend && target_rgb && target_d && stats && n_rays > 0, "loss_partial arguments");
+  return launch_loss_partial(plan, rend, target_rgb, target_d, n_rays, stats, (cudaStream_t)stream);
+}
+
+int nrt_loss_finalize(const NrtPlan* plan, const double* stats, float* losses, void* stream) {
+  NRT_REQUIRE(plan && stats && losses, "loss_finalize arguments");
+  return launch_loss_finalize(stats, losses, (cudaStream_t)stream);
+}
+
+int nrt_loss_fwd(const NrtPlan* plan, const NrtRenderOut* rend, const float* target_rgb, const float* target_d,
+                 int64_t n_rays, double* stats, float* losses, void* stream) {
+  if (int rc = nrt_loss_partial(plan, rend, target_rgb, target_d, n_rays, stats, stream)) return rc;
+  return nrt_loss_finalize(plan, stats, losses, stream);
+}
+
+int nrt_decode_bwd(const NrtPlan* plan, const NrtParams* params, const float* x, int64_t n, const float* draw,
+                   const NrtGrads* grads, void* workspace, void* stream) {
+  NRT_REQUIRE(plan && x && draw && grads && workspace && n > 0, "decode_bwd arguments");
+  if (int rc = check_params(params)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* feat = reinterpret_cast<float*>(workspace);          // [n,32] recomputed features, then overwritten by dfeat
+  if (int rc = launch_encode_fwd(plan, params->grid, x, n, feat, st)) return rc;
+  PointSource src{x, nullptr, nullptr, nullptr, 1};
+  if (int rc = launch_decode_bwd(plan, params, src, n, feat, draw, feat, grads, st)) return rc;
+  if (grads->grid) return launch_encode_bwd(plan, params->grid, src, n, feat, 1.0f, grads->grid, nullptr, st);
+  return NRT_OK;
+}
+
+int64_t nrt_render_bwd_workspace(const NrtPlan* plan, int64_t n_rays) {
+  if (!plan || n_rays < 0) return 0;
+  return n_rays * plan->dev.S * (5 + NRT_ENC) * (int64_t)sizeof(float);
+}
+
+int nrt_render_bwd(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
+                   const float* target_rgb, const float* target_d, int64_t n_rays, const NrtRenderOut* rend,
+                   const double* stats, const float* loss_grad, const NrtGrads* grads, void* workspace, void* stream) {
+  NRT_REQUIRE(plan && rays_o && rays_d && target_rgb && target_d && rend && stats && loss_grad && grads && workspace && n_rays > 0,
+              "render_bwd arguments");
+  NRT_REQUIRE(rend->z_vals && rend->raw && rend->feat, "render_bwd needs z_vals, raw and feat saved by render_fwd");
+  if (int rc = check_params(params)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_pts = n_rays * plan->dev.S;
+  float* draw = reinterpret_cast<float*>(workspace);
+  float* dfeat = draw + n_pts * 5;
+  if (int rc = launch_composite_bwd(plan, rend, target_rgb, target_d, n_rays, stats, loss_grad, draw, st)) return rc;
+  PointSource src{nullptr, rays_o, rays_d, rend->z_vals, plan->dev.S};
+  if (int rc = launch_decode_bwd(plan, params, src, n_pts, rend->feat, draw, dfeat, grads, st)) return rc;
+  if (grads->grid) return launch_encode_bwd(plan, params->grid, src, n_pts, dfeat, 1.0f, grads->grid, nullptr, st);
+  return NRT_OK;
+}
+
+int64_t nrt_smooth_workspace(const NrtPlan* plan, int32_t n) {
+  if (!plan || n < 2) return 0;
+  const int64_t m = n - 1;
+  return m * m * m * NRT_ENC * (int64_t)sizeof(float);
+}
+
+int nrt_smooth_fwd_bwd(const NrtPlan* plan, const float* grid, const float* rand6, int32_t n, double voxel, double margin,
+                       float loss_scale, float* loss, float* dgrid, void* workspace, void* stream) {
+  NRT_REQUIRE(plan && grid && rand6 && loss && workspace && n >= 2, "smooth arguments");
+  return launch_smooth(plan, grid, rand6, n, voxel, margin, loss_scale, loss, dgrid, workspace, (cudaStream_t)stream);
+}
+
+int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,
+                  const int32_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int zero_grad,
+                  void* stream) {
+  NRT_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev), "adam arguments");
+  int sms = 148;
+  return launch_adam(param, grad, exp_avg, exp_avg_sq, n, step, step_dev, lr, beta1, beta2, eps, weight_decay, zero_grad, sms,
+                     (cudaStream_t)stream);
+}
+
+int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream) {
+  NRT_REQUIRE(counter_dev, "null counter");
+  return launch_counter_add(counter_dev, delta, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,552 @@
+// Shared device-side definitions for the naruto_b200 kernels (sm_100a).
+//
+// Fixed network shape (identical at every shipped NARUTO config: configs/Replica/replica_coslam.yaml:44-63,
+// configs/MP3D/mp3d_coslam.yaml:44-63): 16-level x 2-feature hash grid, OneBlob-16 on 3 dims,
+// SDF net 80->32->16 and colour net 63->32->3, bias-free with ReLU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "naruto_b200.h"
+
+#define NRT_L 16          // hash levels
+#define NRT_ENC 32        // hash feature width (L * 2)
+#define NRT_BINS 16       // OneBlob bins per dim
+#define NRT_OB 48         // OneBlob width
+#define NRT_H 32          // hidden width of both MLPs
+#define NRT_O 16          // SDF net output width: sdf + 15 geo
+#define NRT_GEO 15
+#define NRT_IN1 80        // 32 hash + 48 oneblob
+#define NRT_IN3 63        // 48 oneblob + 15 geo
+#define NRT_SMAX 256      // max samples per ray the ray kernels are built for
+
+// smem weight block (floats). Forward part first; the backward kernels append the untransposed copies.
+#define SW_W1T 0                       // [80][32]  W1T[k][j] = w1[j][k]
+#define SW_W2T (SW_W1T + 80 * 32)      // [32][16]  W2T[j][i] = w2[i][j]
+#define SW_W3T (SW_W2T + 32 * 16)      // [64][32]  W3T[k][j] = w3[j][k], row 63 = 0
+#define SW_W4T (SW_W3T + 64 * 32)      // [32][4]   W4T[j][i] = w4[i][j], i = 3 -> 0
+#define SW_FWD_FLOATS (SW_W4T + 32 * 4)
+#define SW_W2 (SW_FWD_FLOATS)          // [16][32]  w2 as stored
+#define SW_W4 (SW_W2 + 16 * 32)        // [4][32]   w4 as stored, row 3 = 0
+#define SW_BWD_FLOATS (SW_W4 + 4 * 32)
+
+struct DevLevel {
+  float scale;        // tcnn grid_scale(level)
+  uint32_t res;       // tcnn grid_resolution(scale)
+  uint32_t size;      // entries in this level (hashmap_size)
+  uint32_t offset;    // first entry of this level in the flat table
+  uint32_t hashed;    // 1: coherent prime hash, 0: dense stride walk
+  uint32_t res2;      // res*res (mod 2^32)
+};
+
+struct DevPlan {
+  DevLevel lv[NRT_L];
+  float bb_min[3];
+  float bb_ext[3];      // float32(bound_max) - float32(bound_min), as the reference's tensor op gives
+  int ud[3];            // uncert grid dims [Nx,Ny,Nz]
+  float trunc;          // training.trunc
+  float sc_trunc;       // float32(sc_factor * trunc)
+  float near_z, far_z, depth_trunc, range_d;
+  int n_d, n_r, S;
+};
+
+struct NrtPlan {
+  NrtConfig cfg;
+  DevPlan dev;
+  int64_t n_grid_floats;
+  int sm_count;
+};
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ldg_f2(const float2* p) { return __ldg(p); }
+
+__device__ __forceinline__ void red_add_f2(float2* addr, float a, float b) {
+  // vectorised no-return atomic: one L2 RMW for both features of an entry
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float softplusf_(float x) {
+  // torch.nn.Softplus(beta=1, threshold=20)
+  return x > 20.0f ? x : log1pf(expf(x));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Philox4x32-10 (counter-based; the in-kernel stand-in for the reference's torch.rand draw)
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// ---------------------------------------------------------------------------------------------
+// hash grid level addressing (tcnn grid.h: pos_fract + grid_index + coherent_prime_hash)
+// ---------------------------------------------------------------------------------------------
+struct LevelPos {
+  uint32_t g[3];
+  float f[3];
+};
+
+__device__ __forceinline__ LevelPos level_pos(const DevLevel& L, float x0, float x1, float x2) {
+  LevelPos p;
+  float xs[3] = {x0, x1, x2};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float pos = fmaf(L.scale, xs[d], 0.5f);
+    float fl = floorf(pos);
+    p.g[d] = (uint32_t)(int)fl;
+    p.f[d] = pos - fl;
+  }
+  return p;
+}
+
+__device__ __forceinline__ uint32_t level_index(const DevLevel& L, uint32_t cx, uint32_t cy, uint32_t cz) {
+  if (L.hashed) {
+    uint32_t h = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+    return h & (L.size - 1u);            // hashed levels always hold exactly 2^T entries
+  }
+  uint32_t idx = cx + cy * L.res + cz * L.res2;
+  // in-bound points give idx < 2*size (vertex coordinate <= res); the full modulo is the rare path
+  if (idx >= L.size) {
+    idx -= L.size;
+    if (idx >= L.size) idx %= L.size;
+  }
+  return idx;
+}
+
+// trilinear weight of corner c (bit d of c selects the +1 vertex along dim d), multiplied in dim order
+__device__ __forceinline__ float corner_weight(const LevelPos& p, int c) {
+  float w = (c & 1) ? p.f[0] : 1.0f - p.f[0];
+  w *= (c & 2) ? p.f[1] : 1.0f - p.f[1];
+  w *= (c & 4) ? p.f[2] : 1.0f - p.f[2];
+  return w;
+}
+
+// gathers one level: returns the two interpolated features
+__device__ __forceinline__ float2 level_gather(const DevLevel& L, const float2* __restrict__ grid, float x0, float x1,
+                                               float x2) {
+  LevelPos p = level_pos(L, x0, x1, x2);
+  const float2* base = grid + L.offset;
+  float2 v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t idx = level_index(L, p.g[0] + (c & 1), p.g[1] + ((c >> 1) & 1), p.g[2] + ((c >> 2) & 1));
+    v[c] = ldg_f2(base + idx);
+  }
+  float2 r = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w = corner_weight(p, c);
+    r.x = fmaf(w, v[c].x, r.x);
+    r.y = fmaf(w, v[c].y, r.y);
+  }
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// uncertainty grid: torch grid_sample(vol[1,1,Nx,Ny,Nz], 2x-1, align_corners=False, zeros), with the
+// reference's un-permuted coordinate order (x -> Nz axis, y -> Ny, z -> Nx)
+// ---------------------------------------------------------------------------------------------
+struct UncertPos {
+  int i[3];      // floor index along the axis addressed by x, y, z (sizes Nz, Ny, Nx)
+  float f[3];
+};
+
+__device__ __forceinline__ UncertPos uncert_pos(const DevPlan& P, float x0, float x1, float x2) {
+  UncertPos u;
+  float xs[3] = {x0, x1, x2};
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float g = __fsub_rn(__fmul_rn(xs[d], 2.0f), 1.0f);
+    float size = (float)P.ud[2 - d];
+    float c = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(g, 1.0f), size), 1.0f), 0.5f);
+    float fl = floorf(c);
+    u.i[d] = (int)fl;
+    u.f[d] = c - fl;
+  }
+  return u;
+}
+
+// linear offset of corner c, or -1 when the corner is outside the volume (zero padding)
+__device__ __forceinline__ int uncert_corner(const DevPlan& P, const UncertPos& u, int c, float& w) {
+  int iz = u.i[0] + (c & 1), iy = u.i[1] + ((c >> 1) & 1), ix = u.i[2] + ((c >> 2) & 1);
+  w = ((c & 1) ? u.f[0] : 1.0f - u.f[0]) * ((c & 2) ? u.f[1] : 1.0f - u.f[1]) * ((c & 4) ? u.f[2] : 1.0f - u.f[2]);
+  bool ok = (unsigned)iz < (unsigned)P.ud[2] && (unsigned)iy < (unsigned)P.ud[1] && (unsigned)ix < (unsigned)P.ud[0];
+  return ok ? (ix * P.ud[1] + iy) * P.ud[2] + iz : -1;
+}
+
+__device__ __forceinline__ float uncert_sample(const DevPlan& P, const float* __restrict__ ug, float x0, float x1,
+                                               float x2) {
+  UncertPos u = uncert_pos(P, x0, x1, x2);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float w;
+    int off = uncert_corner(P, u, c, w);
+    float v = off >= 0 ? __ldg(ug + off) : 0.f;
+    acc = fmaf(w, v, acc);
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// OneBlob (tcnn oneblob.h): 16 bins of one coordinate
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float quartic_cdf(float t) {
+  float u = t * (float)NRT_BINS;
+  float u2 = u * u;
+  float u4 = u2 * u2;
+  float v = (15.0f / 16.0f) * u * (1.0f - (float)(2.0 / 3.0) * u2 + (float)(1.0 / 5.0) * u4) + 0.5f;
+  return fminf(fmaxf(v, 0.0f), 1.0f);
+}
+__device__ __forceinline__ float quartic_pdf(float t) {   // d quartic_cdf / dt
+  float u = t * (float)NRT_BINS;
+  float u2 = u * u;
+  if (u2 > 1.0f) return 0.0f;
+  float m = 1.0f - u2;
+  return (15.0f / 16.0f) * m * m * (float)NRT_BINS;
+}
+__device__ __forceinline__ float wrapped_cdf(float t) { return quartic_cdf(t) + quartic_cdf(t - 1.0f) + quartic_cdf(t + 1.0f); }
+
+__device__ __forceinline__ void oneblob16(float x, float* __restrict__ bins) {
+  float left = wrapped_cdf(0.0f - x);
+  const float first = left;
+#pragma unroll
+  for (int b = 0; b < NRT_BINS; ++b) {
+    float right = (b == NRT_BINS - 1) ? first + 1.0f : wrapped_cdf((float)(b + 1) * (1.0f / NRT_BINS) - x);
+    bins[b] = right - left;
+    left = right;
+  }
+}
+
+// normalisation to the bound (tp/model/scene_rep.py:172-173): two roundings, like the tensor ops
+__device__ __forceinline__ float normalise1(const DevPlan& P, int d, float p) {
+  return __fdiv_rn(__fsub_rn(p, P.bb_min[d]), P.bb_ext[d]);
+}
+
+// cooperative load of the MLP weights into the smem layout above; call from all threads, then sync
+__device__ __forceinline__ void load_weights_smem(float* sw, const NrtParams& prm, bool with_bwd) {
+  for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) {
+    int k = i >> 5, j = i & 31;
+    sw[SW_W1T + i] = __ldg(prm.w1 + j * 80 + k);
+  }
+  for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
+    int j = i >> 4, o = i & 15;
+    sw[SW_W2T + i] = __ldg(prm.w2 + o * 32 + j);
+  }
+  for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
+    int k = i >> 5, j = i & 31;
+    sw[SW_W3T + i] = k < 63 ? __ldg(prm.w3 + j * 63 + k) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 32 * 4; i += blockDim.x) {
+    int j = i >> 2, o = i & 3;
+    sw[SW_W4T + i] = o < 3 ? __ldg(prm.w4 + o * 32 + j) : 0.f;
+  }
+  if (with_bwd) {
+    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) sw[SW_W2 + i] = __ldg(prm.w2 + i);
+    for (int i = threadIdx.x; i < 4 * 32; i += blockDim.x) sw[SW_W4 + i] = i < 96 ? __ldg(prm.w4 + i) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-point decode (thread = point): hash gather -> OneBlob -> SDF net -> colour net.
+// The K dimension of layer 1 is streamed: each feature is folded into the 32 accumulators as soon as it
+// exists, and the OneBlob part of the colour net's first layer is accumulated in the same sweep, so no
+// encoding vector is ever held in registers.
+// ---------------------------------------------------------------------------------------------
+struct PointOut {
+  float rgb[3];     // colour logits
+  float sdf;
+  float unc;        // raw uncertainty sample
+  float geo[NRT_GEO];
+};
+
+__device__ __forceinline__ void fma_row32(float v, const float* __restrict__ row, float* __restrict__ acc) {
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 w = r4[q];
+    acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
+    acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
+    acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
+    acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+  }
+}
+
+template <bool COLOR>
+__device__ __forceinline__ void decode_point(const DevPlan& P, const float* __restrict__ sw,
+                                             const float2* __restrict__ grid, const float* __restrict__ ug, float x0,
+                                             float x1, float x2, float* __restrict__ feat_out, PointOut& out) {
+  float h[NRT_H];
+  float a3[NRT_H];
+#pragma unroll
+  for (int j = 0; j < NRT_H; ++j) {
+    h[j] = 0.f;
+    a3[j] = 0.f;
+  }
+  // --- hash levels -> layer 1 ---
+#pragma unroll
+  for (int l = 0; l < NRT_L; ++l) {
+    float2 f = level_gather(P.lv[l], grid, x0, x1, x2);
+    if (feat_out) reinterpret_cast<float2*>(feat_out)[l] = f;
+    fma_row32(f.x, sw + SW_W1T + (2 * l) * 32, h);
+    fma_row32(f.y, sw + SW_W1T + (2 * l + 1) * 32, h);
+  }
+  out.unc = uncert_sample(P, ug, x0, x1, x2);
+  // --- OneBlob -> layer 1 (rows 32..79) and colour layer 1 (rows 0..47) ---
+  {
+    float xs[3] = {x0, x1, x2};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float bins[NRT_BINS];
+      oneblob16(xs[d], bins);
+#pragma unroll
+      for (int b = 0; b < NRT_BINS; ++b) {
+        fma_row32(bins[b], sw + SW_W1T + (NRT_ENC + d * NRT_BINS + b) * 32, h);
+        if (COLOR) fma_row32(bins[b], sw + SW_W3T + (d * NRT_BINS + b) * 32, a3);
+      }
+    }
+  }
+  // --- SDF net layer 2 ---
+  float o[NRT_O];
+#pragma unroll
+  for (int i = 0; i < NRT_O; ++i) o[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NRT_H; ++j) {
+    float v = fmaxf(h[j], 0.f);
+    const float4* r4 = reinterpret_cast<const float4*>(sw + SW_W2T + j * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 w = r4[q];
+      o[4 * q + 0] = fmaf(v, w.x, o[4 * q + 0]);
+      o[4 * q + 1] = fmaf(v, w.y, o[4 * q + 1]);
+      o[4 * q + 2] = fmaf(v, w.z, o[4 * q + 2]);
+      o[4 * q + 3] = fmaf(v, w.w, o[4 * q + 3]);
+    }
+  }
+  out.sdf = o[0];
+#pragma unroll
+  for (int k = 0; k < NRT_GEO; ++k) out.geo[k] = o[1 + k];
+  if (COLOR) {
+#pragma unroll
+    for (int k = 0; k < NRT_GEO; ++k) fma_row32(o[1 + k], sw + SW_W3T + (NRT_OB + k) * 32, a3);
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NRT_H; ++j) {
+      float v = fmaxf(a3[j], 0.f);
+      float4 w = *reinterpret_cast<const float4*>(sw + SW_W4T + j * 4);
+      c0 = fmaf(v, w.x, c0);
+      c1 = fmaf(v, w.y, c1);
+      c2 = fmaf(v, w.z, c2);
+    }
+    out.rgb[0] = c0;
+    out.rgb[1] = c1;
+    out.rgb[2] = c2;
+  } else {
+    out.rgb[0] = out.rgb[1] = out.rgb[2] = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// depth sampling for one ray, executed by one warp (src/slam/coslam/model/scene_rep.py:158-180).
+// z (smem, length S) receives the sorted (and optionally jittered) depths.
+// torch.linspace semantics: step=(end-start)/(steps-1); i < steps/2 ? start+step*i : end-step*(steps-1-i)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
+  if (steps == 1) return start;
+  float step = __fdiv_rn(__fsub_rn(end, start), (float)(steps - 1));
+  return i < steps / 2 ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(steps - 1 - i)));
+}
+
+__device__ __forceinline__ void warp_sample_z(const DevPlan& P, float td, const float* __restrict__ u_row, int perturb,
+                                              uint64_t seed, int64_t ray, float* __restrict__ z, int lane) {
+  const int nd = P.n_d, nr = P.n_r, S = P.S;
+  const bool invalid = td <= 0.0f;       // reference: z_samples[target_d <= 0] = linspace(near, far)
+  // near-surface ladder value j
+  auto near_val = [&](int j) -> float {
+    return invalid ? linspace_at(P.near_z, P.far_z, nr, j) : __fadd_rn(linspace_at(-P.range_d, P.range_d, nr, j), td);
+  };
+  // stable merge by rank: uniform ladder first on ties
+  for (int i = lane; i < nd; i += 32) {
+    float v = linspace_at(P.near_z, P.far_z, nd, i);
+    int below = 0;
+    for (int j = 0; j < nr; ++j) below += near_val(j) < v ? 1 : 0;
+    z[i + below] = v;
+  }
+  for (int j = lane; j < nr; j += 32) {
+    float v = near_val(j);
+    int le = 0;
+    if (nd > 0) {
+      // count uniform samples <= v: guess from the spacing, then correct with the exact ladder values
+      float step = nd > 1 ? (P.far_z - P.near_z) / (float)(nd - 1) : 1.0f;
+      int g = (int)floorf((v - P.near_z) / step) + 1;
+      g = max(0, min(nd, g));
+      while (g < nd && linspace_at(P.near_z, P.far_z, nd, g) <= v) ++g;
+      while (g > 0 && linspace_at(P.near_z, P.far_z, nd, g - 1) > v) --g;
+      le = g;
+    }
+    z[j + le] = v;
+  }
+  __syncwarp();
+  if (perturb) {
+    // stratified jitter between neighbouring mid-points; read all neighbours before anyone writes
+    float lo[NRT_SMAX / 32], hi[NRT_SMAX / 32];
+#pragma unroll
+    for (int p = 0; p < NRT_SMAX / 32; ++p) {
+      int s = p * 32 + lane;
+      if (s < S) {
+        float zc = z[s];
+        lo[p] = s > 0 ? 0.5f * (zc + z[s - 1]) : zc;
+        hi[p] = s < S - 1 ? 0.5f * (z[s + 1] + zc) : zc;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < NRT_SMAX / 32; ++p) {
+      int s = p * 32 + lane;
+      if (s < S) {
+        float r;
+        if (u_row) {
+          r = u_row[s];
+        } else {
+          uint4 ctr = make_uint4((uint32_t)ray, (uint32_t)(ray >> 32), (uint32_t)(s >> 2), 0u);
+          uint4 rnd = philox4x32(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+          uint32_t pick = (s & 3) == 0 ? rnd.x : (s & 3) == 1 ? rnd.y : (s & 3) == 2 ? rnd.z : rnd.w;
+          r = u32_to_unit(pick);
+        }
+        z[s] = __fadd_rn(lo[p], __fmul_rn(__fsub_rn(hi[p], lo[p]), r));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-ray compositing by one warp (tp/model/scene_rep.py:64-84 + src/slam/coslam/model/scene_rep.py:66-96).
+// raw: smem [S][5], z: smem [S].  Every lane returns the same RayOut.
+// ---------------------------------------------------------------------------------------------
+struct RayOut {
+  float rgb[3], depth, depth_var, acc, disp, uncert;
+  float wsum;        // sum of masked bell weights (before the 1e-8)
+  float z_cut;       // z_surf + sc*trunc
+};
+
+__device__ __forceinline__ float bell_weight(float sdf, float trunc) {
+  float a = __fdiv_rn(sdf, trunc);
+  return sigmoidf_(a) * sigmoidf_(-a);
+}
+
+__device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, const float* __restrict__ raw,
+                                                 const float* __restrict__ z, float* __restrict__ w_out, int lane) {
+  // first sign change (argmax of the 0/1 mask -> 0 when there is none)
+  int first = 0x7fffffff;
+  for (int s = lane; s < S - 1; s += 32) {
+    if (raw[(s + 1) * 5 + 3] * raw[s * 5 + 3] < 0.0f) {
+      first = s;
+      break;
+    }
+  }
+  first = warp_min_i(first);
+  if (first == 0x7fffffff) first = 0;
+  RayOut r;
+  r.z_cut = __fadd_rn(z[first], P.sc_trunc);
+  float ws = 0.f;
+  for (int s = lane; s < S; s += 32)
+    if (z[s] < r.z_cut) ws += bell_weight(raw[s * 5 + 3], P.trunc);
+  ws = warp_sum(ws);
+  r.wsum = ws;
+  const float denom = ws + 1e-8f;
+  float c0 = 0, c1 = 0, c2 = 0, dep = 0, acc = 0, unc = 0;
+  for (int s = lane; s < S; s += 32) {
+    float w = z[s] < r.z_cut ? __fdiv_rn(bell_weight(raw[s * 5 + 3], P.trunc), denom) : 0.f;
+    if (w_out) w_out[s] = w;
+    c0 = fmaf(w, sigmoidf_(raw[s * 5 + 0]), c0);
+    c1 = fmaf(w, sigmoidf_(raw[s * 5 + 1]), c1);
+    c2 = fmaf(w, sigmoidf_(raw[s * 5 + 2]), c2);
+    dep = fmaf(w, z[s], dep);
+    acc += w;
+    unc = fmaf(w * w, softplusf_(raw[s * 5 + 4]) + 0.01f, unc);
+  }
+  r.rgb[0] = warp_sum(c0);
+  r.rgb[1] = warp_sum(c1);
+  r.rgb[2] = warp_sum(c2);
+  r.depth = warp_sum(dep);
+  r.acc = warp_sum(acc);
+  r.uncert = warp_sum(unc);
+  float var = 0.f;
+  for (int s = lane; s < S; s += 32) {
+    float w = z[s] < r.z_cut ? __fdiv_rn(bell_weight(raw[s * 5 + 3], P.trunc), denom) : 0.f;
+    float dz = z[s] - r.depth;
+    var = fmaf(w, dz * dz, var);
+  }
+  r.depth_var = warp_sum(var);
+  r.disp = 1.0f / fmaxf(1e-10f, __fdiv_rn(r.depth, r.acc));
+  return r;
+}
+
+// where the points of a launch come from: an explicit [n,3] array, or rays + depths
+struct PointSource {
+  const float* x;                 // [n,3] normalised points, or NULL -> rays
+  const float* rays_o;
+  const float* rays_d;
+  const float* z;                 // [B,S]
+  int S;
+};
+
+__device__ __forceinline__ void fetch_point(const DevPlan& P, const PointSource& src, int64_t pt, float& x0, float& x1,
+                                            float& x2) {
+  if (src.x) {
+    x0 = __ldg(src.x + pt * 3);
+    x1 = __ldg(src.x + pt * 3 + 1);
+    x2 = __ldg(src.x + pt * 3 + 2);
+  } else {
+    const int64_t ray = pt / src.S;
+    const float zz = __ldg(src.z + pt);
+    x0 = normalise1(P, 0, __fadd_rn(__ldg(src.rays_o + ray * 3 + 0), __fmul_rn(__ldg(src.rays_d + ray * 3 + 0), zz)));
+    x1 = normalise1(P, 1, __fadd_rn(__ldg(src.rays_o + ray * 3 + 1), __fmul_rn(__ldg(src.rays_d + ray * 3 + 1), zz)));
+    x2 = normalise1(P, 2, __fadd_rn(__ldg(src.rays_o + ray * 3 + 2), __fmul_rn(__ldg(src.rays_d + ray * 3 + 2), zz)));
+  }
+}
+
+// error plumbing (api.cu)
+void nrt_set_error(const char* fmt, ...);
+#define NRT_CUDA_CHECK(expr)                                                          \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      nrt_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return NRT_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+#define NRT_REQUIRE(cond, msg)                         \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      nrt_set_error("invalid argument: %s", msg);     \
+      return NRT_ERR_INVALID;                          \
+    }                                                  \
+  } while (0)

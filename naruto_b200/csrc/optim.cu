@@ -1,0 +1,174 @@
+// Smoothness regulariser (CoSLAM.smoothness, tp/coslam.py:245-269) and the fused Adam step
+// (torch.optim.Adam as configured at src/slam/coslam/coslam.py:409-419, 240-243).
+#include "common.cuh"
+
+// lattice point (i,j,k) of the (n-1)^3 smoothness lattice, normalised to the bound.  Mirrors the reference's
+// op order: pts = (coords + jitter) * voxel + bb_min + offset ; x = (pts - bb_min) / (bb_max - bb_min),
+// offset = rand3 * (extent - (n-1)*voxel - 2*margin) + margin
+struct LatticeSpec {
+  int n;               // smooth_pts; the lattice has (n-1)^3 points
+  float voxel;         // float32(smooth_vox)
+  float grid_size;     // float32((n-1) * smooth_vox), product taken in double like the reference's python scalar
+  float margin;        // float32(smooth_margin)
+  float margin2;       // float32(2 * smooth_margin)
+};
+
+__device__ __forceinline__ float lattice_coord(const DevPlan& P, int d, int i, const float* __restrict__ rnd,
+                                               const LatticeSpec& ls) {
+  const float off_max = __fsub_rn(__fsub_rn(P.bb_ext[d], ls.grid_size), ls.margin2);
+  const float offset = __fadd_rn(__fmul_rn(rnd[d], off_max), ls.margin);
+  float p = __fmul_rn(__fadd_rn((float)i, rnd[3 + d]), ls.voxel);
+  p = __fadd_rn(__fadd_rn(p, P.bb_min[d]), offset);
+  return normalise1(P, d, p);
+}
+
+// pass 1: hash features of every lattice point -> F[m^3][16] (float2), thread = (point, level)
+__global__ void __launch_bounds__(256) smooth_encode_kernel(const __grid_constant__ DevPlan P, const float2* __restrict__ grid,
+                                                            const float* __restrict__ rnd, const LatticeSpec ls,
+                                                            float2* __restrict__ F) {
+  __shared__ DevLevel s_lv[NRT_L];
+  if (threadIdx.x < NRT_L) s_lv[threadIdx.x] = P.lv[threadIdx.x];
+  __syncthreads();
+  const int n = ls.n;
+  const int m = n - 1;
+  int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t pt = tt >> 4;
+  int l = (int)(tt & 15);
+  if (pt >= (int64_t)m * m * m) return;
+  int k = (int)(pt % m), j = (int)((pt / m) % m), i = (int)(pt / ((int64_t)m * m));
+  float x0 = lattice_coord(P, 0, i, rnd, ls);
+  float x1 = lattice_coord(P, 1, j, rnd, ls);
+  float x2 = lattice_coord(P, 2, k, rnd, ls);
+  F[pt * NRT_L + l] = level_gather(s_lv[l], grid, x0, x1, x2);
+}
+
+// pass 2: TV loss + its gradient scattered straight into the table.
+// d/dF[p] of sum over edges (F[p]-F[q])^2 = 2 * sum over neighbours (F[p]-F[q]).
+__global__ void __launch_bounds__(256) smooth_tv_bwd_kernel(const __grid_constant__ DevPlan P, const float* __restrict__ rnd,
+                                                            const LatticeSpec ls, const float2* __restrict__ F,
+                                                            float loss_scale, float* __restrict__ loss, float2* __restrict__ dgrid) {
+  __shared__ DevLevel s_lv[NRT_L];
+  __shared__ float s_red[8];
+  if (threadIdx.x < NRT_L) s_lv[threadIdx.x] = P.lv[threadIdx.x];
+  __syncthreads();
+  const int n = ls.n;
+  const int m = n - 1;
+  const int64_t total = (int64_t)m * m * m;
+  int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t pt = tt >> 4;
+  int l = (int)(tt & 15);
+  float tv = 0.f;
+  if (pt < total) {
+    int idx[3] = {(int)(pt / ((int64_t)m * m)), (int)((pt / m) % m), (int)(pt % m)};
+    const int64_t stride[3] = {(int64_t)m * m, m, 1};
+    const float2 f = F[pt * NRT_L + l];
+    float2 g = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (idx[d] + 1 < m) {
+        float2 q = F[(pt + stride[d]) * NRT_L + l];
+        float ex = f.x - q.x, ey = f.y - q.y;
+        tv += ex * ex + ey * ey;      // each edge counted once, at its lower end
+        g.x += ex;
+        g.y += ey;
+      }
+      if (idx[d] > 0) {
+        float2 q = F[(pt - stride[d]) * NRT_L + l];
+        g.x += f.x - q.x;
+        g.y += f.y - q.y;
+      }
+    }
+    const float inv = 1.0f / ((float)n * (float)n * (float)n);
+    g.x *= 2.0f * inv * loss_scale;
+    g.y *= 2.0f * inv * loss_scale;
+    if (dgrid && (g.x != 0.f || g.y != 0.f)) {
+      float x0 = lattice_coord(P, 0, idx[0], rnd, ls);
+      float x1 = lattice_coord(P, 1, idx[1], rnd, ls);
+      float x2 = lattice_coord(P, 2, idx[2], rnd, ls);
+      const DevLevel& L = s_lv[l];
+      LevelPos p = level_pos(L, x0, x1, x2);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t e = level_index(L, p.g[0] + (c & 1), p.g[1] + ((c >> 1) & 1), p.g[2] + ((c >> 2) & 1));
+        float w = corner_weight(p, c);
+        red_add_f2(dgrid + L.offset + e, w * g.x, w * g.y);
+      }
+    }
+    tv *= inv;
+  }
+  tv = warp_sum(tv);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = tv;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += s_red[w];
+    atomicAdd(loss, v);
+  }
+}
+
+int launch_smooth(const NrtPlan* plan, const float* grid, const float* rnd6, int n, double voxel, double margin,
+                  float loss_scale, float* loss, float* dgrid, void* workspace, cudaStream_t st) {
+  const int m = n - 1;
+  const int64_t threads = (int64_t)m * m * m * NRT_L;
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  float2* F = reinterpret_cast<float2*>(workspace);
+  LatticeSpec ls{n, (float)voxel, (float)((double)(n - 1) * voxel), (float)margin, (float)(2.0 * margin)};
+  NRT_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  smooth_encode_kernel<<<blocks, 256, 0, st>>>(plan->dev, (const float2*)grid, rnd6, ls, F);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  smooth_tv_bwd_kernel<<<blocks, 256, 0, st>>>(plan->dev, rnd6, ls, F, loss_scale, loss, (float2*)dgrid);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Adam.  step_dev (optional) holds the 1-based step count on the device so that a captured CUDA graph can
+// be replayed; otherwise `step` is used.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, int step, const int* __restrict__ step_dev,
+                                                   float lr, float beta1, float beta2, float eps, float wd, int zero_grad) {
+  __shared__ float s_c[2];
+  if (threadIdx.x == 0) {
+    const int st = step_dev ? *step_dev : step;
+    const double bc1 = 1.0 - pow((double)beta1, (double)st);
+    const double bc2 = 1.0 - pow((double)beta2, (double)st);
+    s_c[0] = (float)((double)lr / bc1);          // step_size
+    s_c[1] = (float)sqrt(bc2);                   // bias_correction2_sqrt
+  }
+  __syncthreads();
+  const float step_size = s_c[0], bc2s = s_c[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i], gi = g[i], mi = m[i], vi = v[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    mi = mi + (gi - mi) * (1.0f - beta1);                     // exp_avg.lerp_(grad, 1-beta1)
+    vi = vi * beta2 + (1.0f - beta2) * gi * gi;               // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1-beta2)
+    const float denom = sqrtf(vi) / bc2s + eps;
+    pi = pi - step_size * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+
+__global__ void counter_add_kernel(int* c, int delta) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) *c += delta;
+}
+
+int launch_adam(float* p, float* g, float* m, float* v, int64_t n, int step, const int* step_dev, float lr, float b1, float b2,
+                float eps, float wd, int zero_grad, int sm_count, cudaStream_t st) {
+  if (n == 0) return NRT_OK;
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = (int64_t)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  adam_kernel<<<(unsigned)blocks, 256, 0, st>>>(p, g, m, v, n, step, step_dev, lr, b1, b2, eps, wd, zero_grad);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
+
+int launch_counter_add(int* c, int delta, cudaStream_t st) {
+  counter_add_kernel<<<1, 32, 0, st>>>(c, delta);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
