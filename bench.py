@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- rays/sec of one NARUTO mapping iteration (forward + losses + backward + Adam) at 128 samples/ray.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--rays B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one body of the reference's global_BA loop (src/slam/coslam/coslam.py:364-399) on one ray batch of the
+BASELINE.json configs[1] workload: Replica office_0 shape, 680x1200 synthetic frame, B rays x 128 samples/ray
+(n_samples_d=117 + n_range_d=11), hash_size 16.  Prints ONE JSON line (rank 0).
+
+  value      rays/s with the ray batch already resident in HBM when the timed region starts (CUDA-graph replay)
+  e2e        rays/s through the public API with HOST (pinned) ray buffers: H2D of the packed batch and D2H of the
+             losses inside the timed region
+  roofline   the dominant kernel of the step, timed alone with CUDA events in this process (algorithmic bytes /
+             duration vs the measured HBM copy peak)
+  cpu_baseline   the oracle (torch restatement of the reference's Python) timed on the host cores, bounded sample
+
+--impl reference times the reference's CPU implementation of the same step (the oracle port; the reference tree and
+tinycudann are not on the GPU box) with all host threads.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'rays/sec (128 samples/ray) mapping-iter'
+UNIT = 'rays/s'
+N_SAMPLES_D = 117            # + n_range_d 11 = 128 samples per ray
+S = 128
+BYTES_PER_RAY_FWD = S * 1056 + 60          # hash gather 1024 B + uncert 32 B per point, + ray I/O
+BYTES_PER_POINT_BWD_MLP = 128 + 20 + 128   # decode_bwd: saved features in, dL/draw in, dL/dfeatures out
+BYTES_PER_POINT_SCATTER = 1024 + 128 + 4   # encode_bwd: one RMW per gathered entry + dL/dfeatures + z
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(n_rays, steps, warmup, seed=0):
+    import torch
+    from oracle import naruto_oracle as no
+    from naruto_b200.synthetic import SyntheticFrame
+    spec = no.office0_spec(n_samples_d=N_SAMPLES_D)
+    P = no.init_params(spec, seed=seed).clone(requires_grad=True)
+    opt = no.MappingOptimisers(P)
+    frame = SyntheticFrame(spec.bound, seed=seed)
+    times = []
+    for it in range(warmup + steps):
+        o, d, rgb, td = frame.sample(n_rays)
+        t0 = time.perf_counter()
+        u = torch.rand(n_rays, spec.n_samples)
+        no.mapping_iteration(P, opt, o, d, rgb, td, spec, it, u=u, smooth_draws=(torch.rand(3), torch.rand(1, 1, 1, 3)))
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sum(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n_rays = args.ref_rays
+    total, threads = cpu_reference(n_rays, args.steps, args.warmup)
+    val = n_rays * args.steps / total
+    sample = f'{args.steps} full mapping iterations (fwd+loss+bwd+Adam) of {n_rays} rays x {S} samples on the host'
+    line = {
+        'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+        'config': {'workload': f'Replica office_0 shape, 680x1200 synthetic frame, mapping iteration, {n_rays} rays x {S} samples/ray '
+                               f'(n_samples_d={N_SAMPLES_D}+n_range_d=11), hash_size 16; reference Python path restated in torch '
+                               f'(oracle/naruto_oracle.py) on host cores', 'rays_per_step': n_rays},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def time_kernels(plan, ms, torch, flush, reps=10):
+    """CUDA-event time of each big kernel of the step, launched alone on the current stream, L2 flushed before."""
+    from naruto_b200 import _lib as L
+    import ctypes as C
+    B, Sn = ms.B, plan.S
+    n_pts = B * Sn
+    res = {}
+
+    def timed(fn):
+        ts = []
+        for _ in range(reps):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts)
+
+    res['render_fwd_kernel'] = (timed(lambda: plan.render_fwd(ms.P, ms.rays_o, ms.rays_d, ms.target_d, ms.out, u=ms.u)),
+                                B * BYTES_PER_RAY_FWD)
+    plan.loss_partial(ms.out, ms.target_rgb, ms.target_d, ms.stats)
+    plan.loss_finalize(ms.stats, ms.losses)
+    gsave = ms.grad.clone()
+    t_bwd = timed(lambda: plan.render_bwd(ms.P, ms.rays_o, ms.rays_d, ms.target_rgb, ms.target_d, ms.out, ms.stats, ms.loss_grad,
+                                          ms.G, workspace=ms.ws_bwd))
+    # split the three backward kernels with the dedicated entry points is not possible through the public ABI
+    # without re-running; time the scatter alone and attribute the rest to composite+MLP backward
+    dfeat = ms.ws_bwd[n_pts * 5:n_pts * 37].view(n_pts, 32)
+    xs = _points(ms, torch)
+    t_scatter = timed(lambda: plan.encode_bwd(ms.P.grid, xs, dfeat, ms.G.grid))
+    res['encode_bwd_kernel'] = (t_scatter, n_pts * BYTES_PER_POINT_SCATTER)
+    res['composite_bwd+decode_bwd_kernel'] = (max(t_bwd - t_scatter, 1e-6), n_pts * BYTES_PER_POINT_BWD_MLP)
+    ms.grad.copy_(gsave)
+    return res
+
+
+_PTS = {}
+
+
+def _points(ms, torch):
+    """normalised sample points of the current batch (only for timing the scatter kernel through the public ABI)."""
+    key = id(ms)
+    if key not in _PTS:
+        b = torch.tensor(ms.plan.bound, device=ms.dev)
+        pts = ms.rays_o[:, None, :] + ms.rays_d[:, None, :] * ms.out.z_vals[:, :, None]
+        _PTS[key] = ((pts.reshape(-1, 3) - b[:, 0]) / (b[:, 1] - b[:, 0])).contiguous()
+    return _PTS[key]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from naruto_b200.configs import replica_office0, OFFICE0_BOUND
+    from naruto_b200.field import FieldPlan, FieldTensors
+    from naruto_b200.mapper import MappingStep
+    from naruto_b200.synthetic import SyntheticFrame
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    pg = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        pg = dist.group.WORLD
+    B, K, W = args.rays, args.steps, args.warmup
+
+    cfg = replica_office0(n_samples_d=N_SAMPLES_D)
+    plan = FieldPlan(cfg, OFFICE0_BOUND)
+    assert plan.S == S
+    # random-init weights of the reference architecture: tcnn grid init U(-1e-4,1e-4), torch Linear default init
+    g = torch.Generator().manual_seed(0)
+    lin = lambda o, i: (torch.rand(o, i, generator=g) * 2 - 1) / (i ** 0.5)
+    init = FieldTensors((torch.rand(plan.n_grid_floats, generator=g) * 2 - 1) * 1e-4, lin(32, 80), lin(16, 32), lin(32, 63),
+                        lin(3, 32), torch.full(plan.uncert_dims, 3.0))
+    ms = MappingStep(plan, cfg, B, dev, init=init, process_group=pg, use_graph=not args.no_graph)
+    frame = SyntheticFrame(OFFICE0_BOUND, seed=100 + rank)
+    host_batches = [frame.sample_packed(B, pin=True) for _ in range(W + K)]
+    dev_batches = [hb.to(dev) for hb in host_batches]
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
+
+    def flush():
+        flush_buf.zero_()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def run_phase(host_inputs):
+        """W warm-up + K timed steps.  Each timed step: L2 flush (untimed), then [start] inputs -> step -> result [end]."""
+        evs = []
+        for i in range(W + K):
+            if host_inputs:
+                flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ms.load_packed(host_batches[i])                 # H2D from pinned memory, inside the timed region
+                losses = ms.step()
+                host_losses = losses.to('cpu', non_blocking=False)   # D2H of the step's result (syncs)
+                b.record()
+            else:
+                ms.load_packed(dev_batches[i])                  # already resident in HBM: staged before the timed region
+                flush()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ms.step()
+                b.record()
+            if i == W - 1:
+                barrier()
+            if i >= W:
+                evs.append((a, b))
+        barrier()
+        t = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+        if world > 1:
+            tt = torch.tensor([t], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = tt.item()
+        return t
+
+    # graph capture + lazy init outside any timing
+    ms.load_packed(dev_batches[0])
+    for _ in range(5):
+        ms.step()
+    barrier()
+    it0 = ms.it
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_dev = run_phase(host_inputs=False)
+    t_e2e = run_phase(host_inputs=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    launches = sum(ms.launches_per_iter[(it0 + W + i + 1) % 5 == 0] for i in range(K))
+    finite = bool(torch.isfinite(ms.losses[:5]).all().item())
+    value = world * B * K / t_dev
+    e2e = world * B * K / t_e2e
+
+    roof, kern, cpu = None, None, None
+    if rank == 0:
+        hbm, how = peaks()
+        kt = time_kernels(plan, ms, torch, flush)
+        kern = {k: {'ms': round(v[0], 4), 'algorithmic_GB_per_s': round(v[1] / v[0] / 1e6, 1)} for k, v in kt.items()}
+        top = max(kt, key=lambda k: kt[k][0])
+        ach = kt[top][1] / kt[top][0] / 1e6
+        roof = {'bound': 'hbm', 'kernel': top, 'achieved': round(ach, 1), 'peak': hbm, 'unit': 'GB/s', 'frac': round(ach / hbm, 4),
+                'traffic': None, 'peak_source': how,
+                'note': 'algorithmic bytes (SURVEY 8d) / CUDA-event time of the kernel launched alone, L2 flushed; at hash_size 16 '
+                        'the 6.5 MB table is L2-resident so the gather fraction is an accounting convention',
+                'hash_gather': {'kernel': 'render_fwd_kernel', 'achieved': kern['render_fwd_kernel']['algorithmic_GB_per_s'],
+                                'frac': round(kern['render_fwd_kernel']['algorithmic_GB_per_s'] / hbm, 4)}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_cpu, k_cpu = 1024, 5
+        tot, threads = cpu_reference(n_cpu, k_cpu, 1)
+        cpu = {'value': n_cpu * k_cpu / tot, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+               'sample': f'{k_cpu} mapping iterations of {n_cpu} rays x {S} samples (oracle/naruto_oracle.py, torch CPU, '
+                         f'{os.cpu_count()} host cpus)'}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': 1e3 * t_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': f'Replica office_0 shape, 680x1200 synthetic frame, mapping iteration (render fwd + losses + bwd + '
+                               f'smoothness + Adam), {B} rays/GPU x {S} samples/ray (n_samples_d={N_SAMPLES_D}+n_range_d=11), '
+                               f'hash_size 16, random-init weights',
+                   'rays_per_step_per_gpu': B, 'samples_per_ray': S, 'parallelism': f'ray-sharded dp{world}, grad all-reduce',
+                   'l2': 'explicit 256 MB L2 flush before every timed step', 'cuda_graph': not args.no_graph},
+        'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': 10 * B * 4, 'd2h_bytes_per_step': 8 * 4,
+                'ms_per_step': 1e3 * t_e2e / K},
+        'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'kernels': kern, 'losses_finite': finite,
+    }
+    if cpu is not None:
+        line['cpu_baseline'] = cpu
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--rays', type=int, default=4096, help='rays per GPU per mapping iteration')
+    ap.add_argument('--ref-rays', type=int, default=1024, help='rays per step for --impl reference')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

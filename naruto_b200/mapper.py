@@ -11,6 +11,7 @@ import torch
 
 from . import _lib as L
 from .field import FieldPlan, FieldTensors, RenderBuffers
+from .parallel import reduce_grads, reduce_stats
 
 
 class MappingStep:
@@ -49,10 +50,12 @@ class MappingStep:
                 for dst, src in zip(self.P.as_list(), init.as_list()):
                     dst.copy_(src.detach().to(self.dev))
         # static buffers (graph inputs / outputs)
-        self.rays_o = torch.zeros(self.B, 3, **f32)
-        self.rays_d = torch.zeros(self.B, 3, **f32)
-        self.target_rgb = torch.zeros(self.B, 3, **f32)
-        self.target_d = torch.zeros(self.B, 1, **f32)
+        B = self.B
+        self.inbuf = torch.zeros(10 * B, **f32)         # packed [o | d | rgb | depth]: one H2D copy per iteration
+        self.rays_o = self.inbuf[0:3 * B].view(B, 3)
+        self.rays_d = self.inbuf[3 * B:6 * B].view(B, 3)
+        self.target_rgb = self.inbuf[6 * B:9 * B].view(B, 3)
+        self.target_d = self.inbuf[9 * B:10 * B].view(B, 1)
         self.out = RenderBuffers(self.B, plan.S, self.dev, per_sample=True, feat=True)
         self.u = torch.zeros(self.B, plan.S, **f32)
         self.rand6 = torch.zeros(6, **f32)
@@ -67,6 +70,7 @@ class MappingStep:
         self.unc_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.it = 0
         self.use_graph = use_graph
+        self.external_random = False     # test hook: keep caller-written self.u / self.rand6 instead of drawing
         self._graphs = {}
         self.launches_per_iter = {False: 0, True: 0}
 
@@ -74,22 +78,21 @@ class MappingStep:
     def _body(self, with_uncert_step: bool):
         """The launches of one iteration on the current stream.  Returns how many kernels of ours it launched."""
         p, n = self.plan, 0
-        self.u.uniform_()                                   # the reference's torch.rand(z_vals.shape) draw
-        if self.smooth_on:
-            self.rand6.uniform_()                           # torch.rand(3), torch.rand((1,1,1,3))
+        if not self.external_random:
+            self.u.uniform_()                               # the reference's torch.rand(z_vals.shape) draw
+            if self.smooth_on:
+                self.rand6.uniform_()                       # torch.rand(3), torch.rand((1,1,1,3))
         p.counter_add(self.map_step, 1); n += 1
         p.render_fwd(self.P, self.rays_o, self.rays_d, self.target_d, self.out, u=self.u); n += 1
         p.loss_partial(self.out, self.target_rgb, self.target_d, self.stats); n += 1
-        if self.world > 1:
-            torch.distributed.all_reduce(self.stats[:L.N_STATS_SUM], group=self.pg)
+        reduce_stats(self.stats, self.pg)
         p.loss_finalize(self.stats, self.losses); n += 1
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,
                      self.G, workspace=self.ws_bwd); n += 3
         if self.smooth_on and self.rank == 0:               # ray-independent term: added once, on rank 0
             p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
                              self.smooth_loss, self.G.grid, self.ws_smooth); n += 2
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grad, group=self.pg)
+        reduce_grads(self.grad, self.pg)
         ng, nd = self.n_grid, self.n_dec
         # create_optimizer (src/slam/coslam/coslam.py:409-419): decoder group wd=1e-6, grid group eps=1e-15, betas (0.9,0.99)
         p.adam_step(self.theta[:ng], self.grad[:ng], self.exp_avg[:ng], self.exp_avg_sq[:ng], 0, self.lr_embed, 0.9, 0.99,
@@ -131,6 +134,10 @@ class MappingStep:
         self.rays_d.copy_(rays_d.reshape(self.B, 3), non_blocking=True)
         self.target_rgb.copy_(target_rgb.reshape(self.B, 3), non_blocking=True)
         self.target_d.copy_(target_d.reshape(self.B, 1), non_blocking=True)
+
+    def load_packed(self, buf):
+        """One packed [10*B] host (pinned) or device buffer, see SyntheticFrame.sample_packed."""
+        self.inbuf.copy_(buf, non_blocking=True)
 
     def step(self, rays_o=None, rays_d=None, target_rgb=None, target_d=None):
         """One mapping iteration.  Returns the device tensor of the five losses (no host sync)."""

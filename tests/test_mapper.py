@@ -1,0 +1,107 @@
+"""GPU: the fused mapping iteration (naruto_b200/mapper.py: render fwd, losses, backward, smoothness, Adam incl. the
+every-5th uncertainty-grid step) against the oracle's mapping_iteration (torch autograd + torch.optim.Adam) driven
+with the same uniform draws, eager and as a replayed CUDA graph; plus kernel-level checks of smoothness and Adam."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import naruto_oracle as no
+from oracle.make_golden import synth_rays
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(dev, B, n_samples_d, seed, use_graph):
+    from naruto_b200.configs import replica_office0
+    from naruto_b200.field import FieldPlan, FieldTensors
+    from naruto_b200.mapper import MappingStep
+    sp = no.office0_spec(n_samples_d=n_samples_d)
+    P = no.init_params(sp, seed=seed, grid_range=0.05, uncert_jitter=0.5)
+    cfg = replica_office0(n_samples_d=n_samples_d)
+    plan = FieldPlan(cfg, sp.bound)
+    ms = MappingStep(plan, cfg, B, dev, init=FieldTensors(P.grid, P.w1, P.w2, P.w3, P.w4, P.uncert_grid), use_graph=use_graph)
+    ms.external_random = True
+    return sp, P, ms
+
+
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_mapping_iterations_match_oracle(use_graph):
+    dev = torch.device('cuda:0')
+    B, iters = 96, 6                                  # iteration 5 takes the uncertainty-grid Adam step
+    sp, P, ms = _setup(dev, B, 32, 41, use_graph)
+    Po = P.clone(requires_grad=True)
+    opt = no.MappingOptimisers(Po)
+    g = torch.Generator().manual_seed(77)
+    for it in range(iters):
+        o, d, rgb, td = synth_rays(sp, B, seed=500 + it)
+        u = torch.rand(B, sp.n_samples, generator=g)
+        r6 = torch.rand(6, generator=g)
+        loss_o, ret_o = no.mapping_iteration(Po, opt, o, d, rgb, td, sp, it, u=u, smooth_draws=(r6[:3], r6[3:].view(1, 1, 1, 3)))
+        ms.u.copy_(u)
+        ms.rand6.copy_(r6)
+        losses = ms.step(o.to(dev), d.to(dev), rgb.to(dev), td.to(dev))
+        torch.cuda.synchronize()
+        for k, name in enumerate(('rgb_loss', 'depth_loss', 'sdf_loss', 'fs_loss', 'uncert_loss')):
+            a, b = losses[k].item(), ret_o[name].item()
+            assert abs(a - b) <= 5e-4 * abs(b) + 1e-7, (it, name, a, b)
+        assert abs(ms.total_loss() - loss_o.item()) <= 5e-4 * abs(loss_o.item()), (it, ms.total_loss(), loss_o.item())
+    # parameters after 6 Adam steps.  Adam with eps=1e-15 turns a gradient into ~lr*sign(g), so entries whose
+    # gradient is at rounding-noise level may step the other way: compare distributions, not every entry.
+    for name, a, b, tol, frac in (('w1', ms.P.w1, Po.w1, 2e-3, 0.99), ('w2', ms.P.w2, Po.w2, 2e-3, 0.99),
+                                  ('w3', ms.P.w3, Po.w3, 2e-3, 0.99), ('w4', ms.P.w4, Po.w4, 2e-3, 0.99),
+                                  ('uncert', ms.P.uncert, Po.uncert_grid, 2e-2, 0.99),
+                                  ('grid', ms.P.grid, Po.grid, 2e-3, 0.995)):
+        d_ = (a.detach().cpu() - b.detach()).abs().reshape(-1)
+        ok = (d_ <= tol).float().mean().item()
+        assert ok >= frac, f'{name}: {ok * 100:.3f}% of entries within {tol} (max {d_.max():.3e})'
+    # the uncertainty grid must have moved (lr=1 Adam step at iteration 5) and only then
+    assert (ms.P.uncert.cpu() - P.uncert_grid).abs().max() > 0.1
+    assert ms.launches_per_iter[False] == 11 and ms.launches_per_iter[True] == 13
+
+
+def test_smoothness_vs_oracle():
+    dev = torch.device('cuda:0')
+    sp, P, ms = _setup(dev, 8, 32, 43, False)
+    r6 = torch.rand(6, generator=torch.Generator().manual_seed(5))
+    Pg = P.clone(requires_grad=True)
+    sm = no.smoothness(Pg, sp, r6[:3], r6[3:].view(1, 1, 1, 3))
+    (2.5 * sm).backward()
+    ms.rand6.copy_(r6)
+    ms.grad.zero_()
+    ms.plan.smooth_fwd_bwd(ms.P.grid, ms.rand6, sp.smooth_pts, sp.smooth_vox, sp.smooth_margin, 2.5, ms.smooth_loss, ms.G.grid,
+                           ms.ws_smooth)
+    torch.cuda.synchronize()
+    assert abs(ms.smooth_loss.item() - sm.item()) <= 1e-4 * abs(sm.item())
+    ga, gb = ms.G.grid.cpu(), Pg.grid.grad
+    assert (ga - gb).abs().max() <= 1e-4 * gb.abs().max()
+
+
+def test_adam_kernel_vs_torch():
+    dev = torch.device('cuda:0')
+    from naruto_b200.configs import replica_office0, OFFICE0_BOUND
+    from naruto_b200.field import FieldPlan
+    plan = FieldPlan(replica_office0(), OFFICE0_BOUND)
+    g = torch.Generator().manual_seed(3)
+    n = 100003
+    for kw in (dict(lr=0.01, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0), dict(lr=0.01, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-6),
+               dict(lr=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)):
+        p0 = torch.randn(n, generator=g)
+        pt = p0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([pt], **kw)
+        pk, m, v = p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+        step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        for step in range(1, 5):
+            grad = torch.randn(n, generator=g) * (10.0 ** torch.randint(-8, 1, (n,), generator=g).float())
+            grad[::7] = 0.0
+            pt.grad = grad.clone()
+            opt.step()
+            gk = grad.to(dev)
+            if step % 2:
+                plan.adam_step(pk, gk, m, v, step, kw['lr'], kw['betas'][0], kw['betas'][1], kw['eps'], kw['weight_decay'], zero_grad=True)
+            else:   # device-resident step counter (graph replay path)
+                step_dev.fill_(step)
+                plan.adam_step(pk, gk, m, v, 0, kw['lr'], kw['betas'][0], kw['betas'][1], kw['eps'], kw['weight_decay'], zero_grad=True,
+                               step_dev=step_dev)
+            assert (gk == 0).all()
+            err = (pk.cpu() - pt.detach()).abs().max().item()
+            assert err <= 2e-6 * max(1.0, kw['lr'] * 100), (kw, step, err)
