@@ -215,6 +215,20 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   int zero_grad, void* stream);
 int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream);
 
+/* ---- diagnostics ------------------------------------------------------------------------------- */
+/* Tensor-core self-test (no reference counterpart): one CTA multiplies small fp32 matrices through the same
+ * tcgen05 descriptors / TMEM read-back the MLP kernels use.  All pointers dev, row-major fp32.
+ *   mode 0: d[128,n] = a[128,k] * b[n,k]^T  (k % 8 == 0, n % 16 == 0)
+ *   mode 1: d[k,n]   = a[128 rows,k]^T * b[128 rows,n]  (weight-gradient form, k <= 128 valid output rows, passes = 1)
+ *   mode 2: as mode 0 with the A operand staged in tensor memory
+ * passes = 1 (plain TF32) or 3 (hi/lo split, ~fp32 accuracy).  d always has 128 rows. */
+int nrt_selftest_umma(int mode, const float* a, const float* b, int32_t k, int32_t n, int passes, float* d, void* stream);
+/* Raw probe: a_img / b_img (dev) are copied verbatim into shared memory and multiplied as d[128,n] with the given
+ * descriptor fields (bytes): leading / stride byte offsets, per-k-step start-address advance, MN-major flags. */
+int nrt_selftest_umma_raw(const float* a_img, int32_t a_bytes, const float* b_img, int32_t b_bytes, int32_t n, int32_t ksteps,
+                          int32_t a_mn, int32_t b_mn, int32_t a_lbo, int32_t a_sbo, int32_t a_kstep, int32_t b_lbo, int32_t b_sbo,
+                          int32_t b_kstep, float* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

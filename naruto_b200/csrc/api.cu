@@ -29,6 +29,8 @@ int launch_smooth(const NrtPlan*, const float*, const float*, int, double, doubl
 int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
                 cudaStream_t);
 int launch_counter_add(int*, int, cudaStream_t);
+int launch_umma_selftest(int, const float*, const float*, int, int, int, float*, cudaStream_t);
+int launch_umma_raw(const float*, int, const float*, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
 
 static thread_local char g_err[512] = "";
 
@@ -264,6 +266,19 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream) {
   NRT_REQUIRE(counter_dev, "null counter");
   return launch_counter_add(counter_dev, delta, (cudaStream_t)stream);
+}
+
+int nrt_selftest_umma(int mode, const float* a, const float* b, int32_t k, int32_t n, int passes, float* d, void* stream) {
+  NRT_REQUIRE(a && b && d, "selftest arguments");
+  return launch_umma_selftest(mode, a, b, k, n, passes, d, (cudaStream_t)stream);
+}
+
+int nrt_selftest_umma_raw(const float* a_img, int32_t a_bytes, const float* b_img, int32_t b_bytes, int32_t n, int32_t ksteps,
+                          int32_t a_mn, int32_t b_mn, int32_t a_lbo, int32_t a_sbo, int32_t a_kstep, int32_t b_lbo, int32_t b_sbo,
+                          int32_t b_kstep, float* d, void* stream) {
+  NRT_REQUIRE(a_img && b_img && d, "raw probe arguments");
+  return launch_umma_raw(a_img, a_bytes, b_img, b_bytes, n, ksteps, a_mn, b_mn, a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep, d,
+                         (cudaStream_t)stream);
 }
 
 }  // extern "C"
