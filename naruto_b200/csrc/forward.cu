@@ -1,5 +1,5 @@
-// Forward kernels: hash/OneBlob encodings, point decode (query_sdf / query_color_sdf), depth sampling and
-// the fused render_rays kernel (sample -> encode -> MLPs -> composite), plus the loss statistics.
+// Forward kernels outside the tensor-core path (forward_tc.cu): stand-alone hash/OneBlob encodings (the tcnn seam),
+// depth sampling, compositing of caller-provided samples, and the loss statistics.
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -50,37 +50,6 @@ __global__ void __launch_bounds__(256) oneblob_bwd_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
-// point decode: thread = point
-// ---------------------------------------------------------------------------------------------
-template <bool COLOR>
-__global__ void __launch_bounds__(256, 2) decode_fwd_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
-                                                            const float* __restrict__ x, int64_t n, float* __restrict__ raw,
-                                                            float* __restrict__ sdf_uncert, float* __restrict__ geo) {
-  extern __shared__ __align__(16) float smem[];
-  load_weights_smem(smem, prm, false);
-  __syncthreads();
-  const float2* grid = reinterpret_cast<const float2*>(prm.grid);
-  for (int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pt < n; pt += (int64_t)gridDim.x * blockDim.x) {
-    float x0 = __ldg(x + pt * 3), x1 = __ldg(x + pt * 3 + 1), x2 = __ldg(x + pt * 3 + 2);
-    PointOut o;
-    decode_point<COLOR>(P, smem, grid, prm.uncert, x0, x1, x2, nullptr, o);
-    if (raw) {
-      float* r = raw + pt * 5;
-      r[0] = o.rgb[0];
-      r[1] = o.rgb[1];
-      r[2] = o.rgb[2];
-      r[3] = o.sdf;
-      r[4] = o.unc;
-    }
-    if (sdf_uncert) reinterpret_cast<float2*>(sdf_uncert)[pt] = make_float2(o.sdf, o.unc);
-    if (geo) {
-#pragma unroll
-      for (int k = 0; k < NRT_GEO; ++k) geo[pt * NRT_GEO + k] = o.geo[k];
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // depth sampling only (API parity with render_rays' first half; the render kernel fuses the same code)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sample_z_kernel(const __grid_constant__ DevPlan P, const float* __restrict__ target_d,
@@ -92,70 +61,6 @@ __global__ void __launch_bounds__(256) sample_z_kernel(const __grid_constant__ D
   for (int64_t ray = (int64_t)blockIdx.x * wpb + warp; ray < n_rays; ray += (int64_t)gridDim.x * wpb) {
     warp_sample_z(P, __ldg(target_d + ray), u ? u + ray * P.S : nullptr, perturb, seed, ray, z, lane);
     for (int s = lane; s < P.S; s += 32) z_out[ray * P.S + s] = z[s];
-    __syncwarp();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// fused render_rays: one warp per ray, lanes stride over the samples.
-// smem: [weights | per-warp z[S] | per-warp raw[S][5]]
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 2) render_fwd_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
-                                                            const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                            const float* __restrict__ target_d, int64_t n_rays,
-                                                            const float* __restrict__ z_in, const float* __restrict__ u,
-                                                            int perturb, uint64_t seed, const NrtRenderOut out) {
-  extern __shared__ __align__(16) float smem[];
-  load_weights_smem(smem, prm, false);
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  const int S = P.S;
-  float* z = smem + SW_FWD_FLOATS + warp * (S * 6);
-  float* raw = z + S;
-  const float2* grid = reinterpret_cast<const float2*>(prm.grid);
-
-  for (int64_t ray = (int64_t)blockIdx.x * wpb + warp; ray < n_rays; ray += (int64_t)gridDim.x * wpb) {
-    if (z_in) {
-      for (int s = lane; s < S; s += 32) z[s] = __ldg(z_in + ray * S + s);
-      __syncwarp();
-    } else {
-      warp_sample_z(P, __ldg(target_d + ray), u ? u + ray * S : nullptr, perturb, seed, ray, z, lane);
-    }
-    const float o0 = __ldg(rays_o + ray * 3), o1 = __ldg(rays_o + ray * 3 + 1), o2 = __ldg(rays_o + ray * 3 + 2);
-    const float d0 = __ldg(rays_d + ray * 3), d1 = __ldg(rays_d + ray * 3 + 1), d2 = __ldg(rays_d + ray * 3 + 2);
-    for (int s = lane; s < S; s += 32) {
-      const float zz = z[s];
-      // pts = o + d*z then (pts - bb_min)/(bb_max - bb_min): separate roundings, like the reference's tensor ops
-      float x0 = normalise1(P, 0, __fadd_rn(o0, __fmul_rn(d0, zz)));
-      float x1 = normalise1(P, 1, __fadd_rn(o1, __fmul_rn(d1, zz)));
-      float x2 = normalise1(P, 2, __fadd_rn(o2, __fmul_rn(d2, zz)));
-      PointOut po;
-      decode_point<true>(P, smem, grid, prm.uncert, x0, x1, x2, out.feat ? out.feat + (ray * S + s) * NRT_ENC : nullptr, po);
-      float* r = raw + s * 5;
-      r[0] = po.rgb[0];
-      r[1] = po.rgb[1];
-      r[2] = po.rgb[2];
-      r[3] = po.sdf;
-      r[4] = po.unc;
-    }
-    __syncwarp();
-    RayOut ro = warp_composite(P, S, raw, z, out.weights ? out.weights + ray * S : nullptr, lane);
-    if (lane == 0) {
-      if (out.rgb) {
-        out.rgb[ray * 3 + 0] = ro.rgb[0];
-        out.rgb[ray * 3 + 1] = ro.rgb[1];
-        out.rgb[ray * 3 + 2] = ro.rgb[2];
-      }
-      if (out.depth) out.depth[ray] = ro.depth;
-      if (out.depth_var) out.depth_var[ray] = ro.depth_var;
-      if (out.acc) out.acc[ray] = ro.acc;
-      if (out.disp) out.disp[ray] = ro.disp;
-      if (out.uncert) out.uncert[ray] = ro.uncert;
-    }
-    if (out.z_vals)
-      for (int s = lane; s < S; s += 32) out.z_vals[ray * S + s] = z[s];
-    if (out.raw)
-      for (int i = lane; i < S * 5; i += 32) out.raw[ray * S * 5 + i] = raw[i];
     __syncwarp();
   }
 }
@@ -336,19 +241,6 @@ int launch_oneblob_bwd(const float* x, int64_t n, const float* dout, float* dx, 
   return NRT_OK;
 }
 
-int launch_decode_fwd(const NrtPlan* plan, const NrtParams* prm, const float* x, int64_t n, int with_color, float* raw,
-                      float* sdf_uncert, float* geo, cudaStream_t st) {
-  if (n == 0) return NRT_OK;
-  const size_t smem = SW_FWD_FLOATS * sizeof(float);
-  int blocks = grid_for(n, 256, plan->sm_count, 2);
-  if (with_color)
-    decode_fwd_kernel<true><<<blocks, 256, smem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
-  else
-    decode_fwd_kernel<false><<<blocks, 256, smem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
-  NRT_CUDA_CHECK(cudaGetLastError());
-  return NRT_OK;
-}
-
 int launch_sample_z(const NrtPlan* plan, const float* target_d, int64_t n_rays, const float* u, int perturb, uint64_t seed,
                     float* z, cudaStream_t st) {
   if (n_rays == 0) return NRT_OK;
@@ -363,24 +255,6 @@ int launch_composite_fwd(const NrtPlan* plan, const float* raw, const float* z, 
   if (n_rays == 0) return NRT_OK;
   const size_t smem = (size_t)8 * S * 6 * sizeof(float);
   composite_fwd_kernel<<<grid_for(n_rays, 8, plan->sm_count, 8), 256, smem, st>>>(plan->dev, raw, z, n_rays, S, *out);
-  NRT_CUDA_CHECK(cudaGetLastError());
-  return NRT_OK;
-}
-
-size_t render_fwd_smem(const NrtPlan* plan) { return (SW_FWD_FLOATS + 8 * plan->dev.S * 6) * sizeof(float); }
-
-int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d,
-                      const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
-                      const NrtRenderOut* out, cudaStream_t st) {
-  if (n_rays == 0) return NRT_OK;
-  const size_t smem = render_fwd_smem(plan);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
-  }
-  int blocks = grid_for(n_rays, 8, plan->sm_count, 2);
-  render_fwd_kernel<<<blocks, 256, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, *out);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

@@ -1,0 +1,451 @@
+// Tensor-core forward path: point decode (query_sdf / query_color_sdf) and the fused render_rays kernel.
+//
+// One CTA = 128 threads = one tile of 128 sample points; thread t owns point t = tensor-memory lane t.
+//   SIMT part (per thread): ray march -> normalise -> 16-level hash gather (+ uncertainty trilerp) -> OneBlob;
+//                           the encoded row is split into tf32 hi/lo pieces and staged straight into TMEM (tcgen05.st).
+//   tcgen05 part (one elected thread issues): the four bias-free layers as A[tmem] x B[smem] tf32 MMAs with M=128,
+//                           three passes each (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM) so the result stays within
+//                           ~1e-6 of the fp32 reference; ReLU / re-split epilogues read the accumulator back with tcgen05.ld.
+//   compositing (render kernel): raw = [rgb logits, sdf, uncertainty] of a block of rays is kept in shared memory and
+//                           integrated warp-per-ray with shuffle reductions (sdf2weights + raw2outputs).
+//
+// TMEM columns (256 allocated per CTA, two CTAs per SM):
+//   [0,32)    accumulator of the current layer
+//   [32,128)  A_hi: X0[32] (hash features, later relu(h1), later relu(h3)) | OneBlob[48] | geo[16]
+//   [128,224) A_lo: same structure, the low-order pieces
+// Layer 1 reads A columns X0|OneBlob (K=80), layer 2 reads X0 (K=32), layer 3 reads OneBlob|geo (K=64), layer 4 reads X0.
+//
+// Reference semantics: tp/model/scene_rep.py:160-178 (run_network), src/slam/coslam/model/scene_rep.py:58-64,98-148
+// (calc_embedding / query_sdf / query_color_sdf), src/slam/coslam/model/decoder.py:29-41,99-116, and for the ray kernel
+// src/slam/coslam/model/scene_rep.py:150-225,66-96 with tp/model/scene_rep.py:64-84.
+#include "common.cuh"
+#include "umma.cuh"
+
+using namespace umma;
+
+// shared-memory weight block (floats): chunk-major K-major B operands; the lo pieces follow at +FW_FLOATS
+#define FW_W1 0                   // [20 K-chunks][32 rows j][4]   k: hash 0..31 | oneblob 32..79
+#define FW_W2 (FW_W1 + 80 * 32)   // [ 8][16 rows i][4]            k: h1 0..31
+#define FW_W3 (FW_W2 + 32 * 16)   // [16][32 rows j][4]            k: oneblob 0..47 | geo 48..62 | 0
+#define FW_W4 (FW_W3 + 64 * 32)   // [ 8][16 rows i][4]            rows 3..15 = 0
+#define FW_FLOATS (FW_W4 + 32 * 16)
+
+#define TC_ACC 0
+#define TC_AHI 32
+#define TC_ALO 128
+#define TA_X0 0
+#define TA_OB 32
+#define TA_GEO 80
+#define TC_COLS 256
+
+#define UNIT_PTS_MAX 2048         // sample points of one ray block staged in shared memory
+
+__device__ __forceinline__ void load_weights_tc(float* sw, const NrtParams& prm) {
+  float* lo = sw + FW_FLOATS;
+  for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) {
+    const int j = i / 80, k = i % 80;
+    const float v = __ldg(prm.w1 + i), h = tf32_hi(v);
+    const int o = FW_W1 + ((k >> 2) * 32 + j) * 4 + (k & 3);
+    sw[o] = h;
+    lo[o] = v - h;
+  }
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int r = i >> 5, k = i & 31;
+    const float v = __ldg(prm.w2 + i), h = tf32_hi(v);
+    const int o = FW_W2 + ((k >> 2) * 16 + r) * 4 + (k & 3);
+    sw[o] = h;
+    lo[o] = v - h;
+  }
+  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+    const int j = i >> 6, k = i & 63;
+    const float v = k < 63 ? __ldg(prm.w3 + j * 63 + k) : 0.f, h = tf32_hi(v);
+    const int o = FW_W3 + ((k >> 2) * 32 + j) * 4 + (k & 3);
+    sw[o] = h;
+    lo[o] = v - h;
+  }
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int r = i >> 5, k = i & 31;
+    const float v = r < 3 ? __ldg(prm.w4 + r * 32 + k) : 0.f, h = tf32_hi(v);
+    const int o = FW_W4 + ((k >> 2) * 16 + r) * 4 + (k & 3);
+    sw[o] = h;
+    lo[o] = v - h;
+  }
+}
+
+struct TileCtx {
+  uint32_t tb;         // TMEM base of this CTA
+  uint32_t lane_tb;    // tb + (32*warp << 16): the lanes this warp may touch
+  uint64_t* bar;       // MMA-complete mbarrier
+  uint32_t phase;
+  uint32_t w_hi, w_lo; // shared-memory addresses of the weight blocks
+};
+
+// D[:, 0:N) = A[:, a_col : a_col+K) * W^T in three tf32 passes; issued by one thread, completion -> c.bar
+template <int K, int N>
+__device__ __forceinline__ void issue_layer(const TileCtx& c, int a_col, int w_off) {
+  constexpr uint32_t idesc = idesc_tf32(128, N, 0, 0);
+  const uint32_t d = c.tb + TC_ACC;
+  const uint32_t wh = c.w_hi + w_off * 4, wl = c.w_lo + w_off * 4;
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wh, N, 2 * ks), idesc, ks > 0);
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_ALO + a_col + 8 * ks, desc_kmajor(wh, N, 2 * ks), idesc, true);
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wl, N, 2 * ks), idesc, true);
+  mma_commit(c.bar);
+}
+
+// all threads: publish this thread's TMEM stores, let thread 0 issue the layer, wait for the accumulator
+template <int K, int N>
+__device__ __forceinline__ void run_layer(TileCtx& c, int a_col, int w_off) {
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    issue_layer<K, N>(c, a_col, w_off);
+  }
+  __syncwarp();
+  mbar_wait(c.bar, c.phase);
+  c.phase ^= 1u;
+  tc_fence_after();
+}
+
+// stage 16 consecutive A columns (hi and lo pieces) of this thread's row
+__device__ __forceinline__ void stage16(const TileCtx& c, int col, const float* v) {
+  float hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    hi[i] = tf32_hi(v[i]);
+    lo[i] = v[i] - hi[i];
+  }
+  tmem_st16(c.lane_tb + TC_AHI + col, hi);
+  tmem_st16(c.lane_tb + TC_ALO + col, lo);
+}
+
+// One tile: every thread of the CTA calls this with its own point (inactive threads feed zeros).
+template <bool COLOR>
+__device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const float2* __restrict__ grid,
+                                            const float* __restrict__ ug, bool active, float x0, float x1, float x2,
+                                            float* __restrict__ feat_out, PointOut& out) {
+  // ---- encodings -> TMEM ----
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float f[16];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      float2 v = make_float2(0.f, 0.f);
+      if (active) v = level_gather(P.lv[half * 8 + l], grid, x0, x1, x2);
+      f[2 * l] = v.x;
+      f[2 * l + 1] = v.y;
+    }
+    if (feat_out) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<float4*>(feat_out)[half * 4 + q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    }
+    stage16(c, TA_X0 + 16 * half, f);
+  }
+  {
+    const float xs[3] = {x0, x1, x2};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      float bins[NRT_BINS];
+      oneblob16(xs[d], bins);
+      if (!active) {
+#pragma unroll
+        for (int b = 0; b < NRT_BINS; ++b) bins[b] = 0.f;
+      }
+      stage16(c, TA_OB + 16 * d, bins);
+    }
+  }
+  out.unc = active ? uncert_sample(P, ug, x0, x1, x2) : 0.f;
+  // ---- SDF net ----
+  run_layer<80, 32>(c, TA_X0, FW_W1);
+  {
+    float h[32];
+    tmem_ld16(c.lane_tb + TC_ACC, h);
+    tmem_ld16(c.lane_tb + TC_ACC + 16, h + 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
+    stage16(c, TA_X0, h);
+    stage16(c, TA_X0 + 16, h + 16);
+  }
+  run_layer<32, 16>(c, TA_X0, FW_W2);
+  {
+    float o[16];
+    tmem_ld16(c.lane_tb + TC_ACC, o);
+    tmem_ld_wait();
+    out.sdf = o[0];
+#pragma unroll
+    for (int k = 0; k < NRT_GEO; ++k) out.geo[k] = o[1 + k];
+    if (COLOR) {
+      float g[16];
+#pragma unroll
+      for (int k = 0; k < NRT_GEO; ++k) g[k] = o[1 + k];
+      g[15] = 0.f;
+      stage16(c, TA_GEO, g);
+    }
+  }
+  if (COLOR) {
+    // ---- colour net ----
+    run_layer<64, 32>(c, TA_OB, FW_W3);
+    {
+      float h[32];
+      tmem_ld16(c.lane_tb + TC_ACC, h);
+      tmem_ld16(c.lane_tb + TC_ACC + 16, h + 16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
+      stage16(c, TA_X0, h);
+      stage16(c, TA_X0 + 16, h + 16);
+    }
+    run_layer<32, 16>(c, TA_X0, FW_W4);
+    {
+      float r[4];
+      tmem_ld4(c.lane_tb + TC_ACC, r);
+      tmem_ld_wait();
+      out.rgb[0] = r[0];
+      out.rgb[1] = r[1];
+      out.rgb[2] = r[2];
+    }
+  } else {
+    out.rgb[0] = out.rgb[1] = out.rgb[2] = 0.f;
+  }
+  // No barrier needed before the next tile: its tcgen05.st target only A columns whose last reader (this tile's MMAs)
+  // has completed, and the accumulator is next written by an MMA issued after the next run_layer() barrier.
+}
+
+struct CtaSetup {
+  float* sw;
+  uint64_t* bar;
+  uint32_t* slot;
+};
+
+// common prologue: weights -> smem, barrier init, TMEM allocation.  smem_raw: [bar 8 | slot 4 | pad | weights hi | weights lo | ...]
+__device__ __forceinline__ TileCtx cta_prologue(uint8_t* smem_raw, const NrtParams& prm, float** after_weights) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
+  float* sw = reinterpret_cast<float*>(smem_raw + 128);
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<TC_COLS>(slot);
+  }
+  load_weights_tc(sw, prm);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  TileCtx c;
+  c.tb = *slot;
+  c.lane_tb = c.tb + ((uint32_t)(32 * warp) << 16);
+  c.bar = bar;
+  c.phase = 0u;
+  c.w_hi = smem_u32(sw);
+  c.w_lo = smem_u32(sw + FW_FLOATS);
+  *after_weights = sw + 2 * FW_FLOATS;
+  return c;
+}
+
+__device__ __forceinline__ void cta_epilogue(const TileCtx& c) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc<TC_COLS>(c.tb);
+}
+
+#define TC_SMEM_HEADER 128
+#define TC_SMEM_WEIGHTS (TC_SMEM_HEADER + 2 * FW_FLOATS * 4)
+
+// ---------------------------------------------------------------------------------------------
+// point decode
+// ---------------------------------------------------------------------------------------------
+template <bool COLOR>
+__global__ void __launch_bounds__(128, 2) points_fwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
+                                                               const float* __restrict__ x, int64_t n, float* __restrict__ raw,
+                                                               float* __restrict__ sdf_uncert, float* __restrict__ geo) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  float* rest;
+  TileCtx c = cta_prologue(smem_raw, prm, &rest);
+  const float2* grid = reinterpret_cast<const float2*>(prm.grid);
+  const int64_t n_tiles = (n + 127) / 128;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t pt = tile * 128 + threadIdx.x;
+    const bool active = pt < n;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+    if (active) {
+      x0 = __ldg(x + pt * 3);
+      x1 = __ldg(x + pt * 3 + 1);
+      x2 = __ldg(x + pt * 3 + 2);
+    }
+    PointOut o;
+    decode_tile<COLOR>(P, c, grid, prm.uncert, active, x0, x1, x2, nullptr, o);
+    if (active) {
+      if (raw) {
+        float* r = raw + pt * 5;
+        r[0] = o.rgb[0];
+        r[1] = o.rgb[1];
+        r[2] = o.rgb[2];
+        r[3] = o.sdf;
+        r[4] = o.unc;
+      }
+      if (sdf_uncert) reinterpret_cast<float2*>(sdf_uncert)[pt] = make_float2(o.sdf, o.unc);
+      if (geo) {
+#pragma unroll
+        for (int k = 0; k < NRT_GEO; ++k) geo[pt * NRT_GEO + k] = o.geo[k];
+      }
+    }
+  }
+  cta_epilogue(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused render_rays: a CTA takes blocks of `rpu` consecutive rays (<= UNIT_PTS_MAX sample points);
+// smem after the weights: [ray o,d: rpu*6 | z: rpu*S | raw: rpu*S*5]
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
+                                                               const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                               const float* __restrict__ target_d, int64_t n_rays,
+                                                               const float* __restrict__ z_in, const float* __restrict__ u,
+                                                               int perturb, uint64_t seed, int rpu, const NrtRenderOut out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  float* rest;
+  TileCtx c = cta_prologue(smem_raw, prm, &rest);
+  const int S = P.S;
+  float* s_ray = rest;
+  float* s_z = s_ray + rpu * 6;
+  float* s_raw = s_z + rpu * S;
+  const float2* grid = reinterpret_cast<const float2*>(prm.grid);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_units = (n_rays + rpu - 1) / rpu;
+
+  for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int64_t r0 = unit * rpu;
+    const int nr = (int)min((int64_t)rpu, n_rays - r0);
+    const int npts = nr * S;
+    // ---- stage the rays and their depth samples ----
+    for (int i = threadIdx.x; i < nr * 6; i += 128) {
+      const int rl = i / 6, k = i - rl * 6;
+      s_ray[i] = k < 3 ? __ldg(rays_o + (r0 + rl) * 3 + k) : __ldg(rays_d + (r0 + rl) * 3 + k - 3);
+    }
+    for (int rl = warp; rl < nr; rl += 4) {
+      const int64_t ray = r0 + rl;
+      float* z = s_z + rl * S;
+      if (z_in) {
+        for (int s = lane; s < S; s += 32) z[s] = __ldg(z_in + ray * S + s);
+      } else {
+        warp_sample_z(P, __ldg(target_d + ray), u ? u + ray * S : nullptr, perturb, seed, ray, z, lane);
+      }
+    }
+    __syncthreads();
+    // ---- decode tile by tile ----
+    for (int t0 = 0; t0 < npts; t0 += 128) {
+      const int pl = t0 + threadIdx.x;
+      const bool active = pl < npts;
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+      if (active) {
+        const int rl = pl / S;
+        const float zz = s_z[pl];
+        const float* ry = s_ray + rl * 6;
+        // pts = o + d*z then (pts - bb_min)/(bb_max - bb_min): separate roundings, like the reference's tensor ops
+        x0 = normalise1(P, 0, __fadd_rn(ry[0], __fmul_rn(ry[3], zz)));
+        x1 = normalise1(P, 1, __fadd_rn(ry[1], __fmul_rn(ry[4], zz)));
+        x2 = normalise1(P, 2, __fadd_rn(ry[2], __fmul_rn(ry[5], zz)));
+      }
+      PointOut po;
+      decode_tile<true>(P, c, grid, prm.uncert, active, x0, x1, x2,
+                        (out.feat && active) ? out.feat + (r0 * S + pl) * NRT_ENC : nullptr, po);
+      if (active) {
+        float* r = s_raw + pl * 5;
+        r[0] = po.rgb[0];
+        r[1] = po.rgb[1];
+        r[2] = po.rgb[2];
+        r[3] = po.sdf;
+        r[4] = po.unc;
+      }
+    }
+    __syncthreads();
+    // ---- integrate along each ray ----
+    for (int rl = warp; rl < nr; rl += 4) {
+      const int64_t ray = r0 + rl;
+      const float* z = s_z + rl * S;
+      const float* raw = s_raw + rl * S * 5;
+      RayOut ro = warp_composite(P, S, raw, z, out.weights ? out.weights + ray * S : nullptr, lane);
+      if (lane == 0) {
+        if (out.rgb) {
+          out.rgb[ray * 3 + 0] = ro.rgb[0];
+          out.rgb[ray * 3 + 1] = ro.rgb[1];
+          out.rgb[ray * 3 + 2] = ro.rgb[2];
+        }
+        if (out.depth) out.depth[ray] = ro.depth;
+        if (out.depth_var) out.depth_var[ray] = ro.depth_var;
+        if (out.acc) out.acc[ray] = ro.acc;
+        if (out.disp) out.disp[ray] = ro.disp;
+        if (out.uncert) out.uncert[ray] = ro.uncert;
+      }
+      if (out.z_vals)
+        for (int s = lane; s < S; s += 32) out.z_vals[ray * S + s] = z[s];
+      if (out.raw)
+        for (int i = lane; i < S * 5; i += 32) out.raw[ray * S * 5 + i] = raw[i];
+    }
+    __syncthreads();
+  }
+  cta_epilogue(c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+// Both kernels are held to two CTAs per SM (2 x 256 TMEM columns = the whole tensor memory): the point kernel
+// requests enough dynamic shared memory that a third CTA cannot become resident and then stall in tcgen05.alloc.
+static const size_t kPointsSmem = 80 * 1024;
+
+int launch_decode_fwd(const NrtPlan* plan, const NrtParams* prm, const float* x, int64_t n, int with_color, float* raw,
+                      float* sdf_uncert, float* geo, cudaStream_t st) {
+  if (n == 0) return NRT_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRT_CUDA_CHECK(cudaFuncSetAttribute(points_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPointsSmem));
+    NRT_CUDA_CHECK(cudaFuncSetAttribute(points_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPointsSmem));
+    attr_set = true;
+  }
+  const int64_t tiles = (n + 127) / 128;
+  const int blocks = (int)(tiles < 2 * plan->sm_count ? tiles : 2 * plan->sm_count);
+  if (with_color)
+    points_fwd_tc_kernel<true><<<blocks, 128, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
+  else
+    points_fwd_tc_kernel<false><<<blocks, 128, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
+
+int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d,
+                      const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
+                      const NrtRenderOut* out, cudaStream_t st) {
+  if (n_rays == 0) return NRT_OK;
+  const int S = plan->dev.S;
+  const int slots = 2 * plan->sm_count;
+  // rays per block: as many blocks as there are CTA slots (one balanced wave), capped by the staging buffer
+  int64_t rpu = (n_rays + slots - 1) / slots;
+  const int cap = UNIT_PTS_MAX / S > 1 ? UNIT_PTS_MAX / S : 1;
+  if (rpu > cap) rpu = cap;
+  if (rpu < 1) rpu = 1;
+  const int64_t units = (n_rays + rpu - 1) / rpu;
+  size_t smem = TC_SMEM_WEIGHTS + (size_t)rpu * (6 + 6 * S) * sizeof(float);
+  if (smem < kPointsSmem) smem = kPointsSmem;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    attr_set = true;
+  }
+  const int blocks = (int)(units < slots ? units : slots);
+  render_fwd_tc_kernel<<<blocks, 128, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed,
+                                                  (int)rpu, *out);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
