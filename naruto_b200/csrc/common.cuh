@@ -20,16 +20,6 @@
 #define NRT_IN3 63        // 48 oneblob + 15 geo
 #define NRT_SMAX 256      // max samples per ray the ray kernels are built for
 
-// smem weight block (floats). Forward part first; the backward kernels append the untransposed copies.
-#define SW_W1T 0                       // [80][32]  W1T[k][j] = w1[j][k]
-#define SW_W2T (SW_W1T + 80 * 32)      // [32][16]  W2T[j][i] = w2[i][j]
-#define SW_W3T (SW_W2T + 32 * 16)      // [64][32]  W3T[k][j] = w3[j][k], row 63 = 0
-#define SW_W4T (SW_W3T + 64 * 32)      // [32][4]   W4T[j][i] = w4[i][j], i = 3 -> 0
-#define SW_FWD_FLOATS (SW_W4T + 32 * 4)
-#define SW_W2 (SW_FWD_FLOATS)          // [16][32]  w2 as stored
-#define SW_W4 (SW_W2 + 16 * 32)        // [4][32]   w4 as stored, row 3 = 0
-#define SW_BWD_FLOATS (SW_W4 + 4 * 32)
-
 struct DevLevel {
   float scale;        // tcnn grid_scale(level)
   uint32_t res;       // tcnn grid_resolution(scale)
@@ -244,40 +234,39 @@ __device__ __forceinline__ void oneblob16(float x, float* __restrict__ bins) {
   }
 }
 
+// Same encoding, evaluated sparsely.  With boundary values B_b = wrapped_cdf(b/16 - x) (b = 0..15) and B_16 = B_0 + 1,
+// bins[b] = B_{b+1} - B_b.  For x in [0, 1) and i0 = floor(16 x), the quartic kernel (support |u| < 1, clamped outside)
+// makes every boundary except b = i0, i0 + 1 and the wrap-around boundary b = 0 saturate: B_b = 0 + 0 + 1 for b < i0 and
+// 1 + 0 + 1 for b > i0 + 1.  The three live boundaries are evaluated with the dense formula, so the result equals
+// oneblob16() bit for bit except when x sits within one ulp of a bin boundary (difference <= 6e-8).  x outside [0, 1)
+// (sample points outside the bound) takes the dense path.
+__device__ __forceinline__ void oneblob16_fast(float x, float* __restrict__ bins) {
+  if (!(x >= 0.0f && x < 1.0f)) {
+    oneblob16(x, bins);
+    return;
+  }
+  const int i0 = min((int)(x * (float)NRT_BINS), NRT_BINS - 1);
+  const float c0 = wrapped_cdf(0.0f - x);
+  const float ca = wrapped_cdf((float)i0 * (1.0f / NRT_BINS) - x);
+  const float cb = wrapped_cdf((float)(i0 + 1) * (1.0f / NRT_BINS) - x);
+  const float c16 = c0 + 1.0f;
+  float left = c0;
+#pragma unroll
+  for (int b = 0; b < NRT_BINS; ++b) {
+    const int r = b + 1;
+    const float right = r == NRT_BINS ? c16 : r < i0 ? 1.0f : r == i0 ? ca : r == i0 + 1 ? cb : 2.0f;
+    bins[b] = right - left;
+    left = right;
+  }
+}
+
 // normalisation to the bound (tp/model/scene_rep.py:172-173): two roundings, like the tensor ops
 __device__ __forceinline__ float normalise1(const DevPlan& P, int d, float p) {
   return __fdiv_rn(__fsub_rn(p, P.bb_min[d]), P.bb_ext[d]);
 }
 
-// cooperative load of the MLP weights into the smem layout above; call from all threads, then sync
-__device__ __forceinline__ void load_weights_smem(float* sw, const NrtParams& prm, bool with_bwd) {
-  for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) {
-    int k = i >> 5, j = i & 31;
-    sw[SW_W1T + i] = __ldg(prm.w1 + j * 80 + k);
-  }
-  for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
-    int j = i >> 4, o = i & 15;
-    sw[SW_W2T + i] = __ldg(prm.w2 + o * 32 + j);
-  }
-  for (int i = threadIdx.x; i < 64 * 32; i += blockDim.x) {
-    int k = i >> 5, j = i & 31;
-    sw[SW_W3T + i] = k < 63 ? __ldg(prm.w3 + j * 63 + k) : 0.f;
-  }
-  for (int i = threadIdx.x; i < 32 * 4; i += blockDim.x) {
-    int j = i >> 2, o = i & 3;
-    sw[SW_W4T + i] = o < 3 ? __ldg(prm.w4 + o * 32 + j) : 0.f;
-  }
-  if (with_bwd) {
-    for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) sw[SW_W2 + i] = __ldg(prm.w2 + i);
-    for (int i = threadIdx.x; i < 4 * 32; i += blockDim.x) sw[SW_W4 + i] = i < 96 ? __ldg(prm.w4 + i) : 0.f;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// per-point decode (thread = point): hash gather -> OneBlob -> SDF net -> colour net.
-// The K dimension of layer 1 is streamed: each feature is folded into the 32 accumulators as soon as it
-// exists, and the OneBlob part of the colour net's first layer is accumulated in the same sweep, so no
-// encoding vector is ever held in registers.
+// per-point decode result (the MLPs themselves run on the tensor cores: mlp_tc.cuh / forward_tc.cu)
 // ---------------------------------------------------------------------------------------------
 struct PointOut {
   float rgb[3];     // colour logits
@@ -285,92 +274,6 @@ struct PointOut {
   float unc;        // raw uncertainty sample
   float geo[NRT_GEO];
 };
-
-__device__ __forceinline__ void fma_row32(float v, const float* __restrict__ row, float* __restrict__ acc) {
-  const float4* r4 = reinterpret_cast<const float4*>(row);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float4 w = r4[q];
-    acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
-    acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
-    acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
-    acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
-  }
-}
-
-template <bool COLOR>
-__device__ __forceinline__ void decode_point(const DevPlan& P, const float* __restrict__ sw,
-                                             const float2* __restrict__ grid, const float* __restrict__ ug, float x0,
-                                             float x1, float x2, float* __restrict__ feat_out, PointOut& out) {
-  float h[NRT_H];
-  float a3[NRT_H];
-#pragma unroll
-  for (int j = 0; j < NRT_H; ++j) {
-    h[j] = 0.f;
-    a3[j] = 0.f;
-  }
-  // --- hash levels -> layer 1 ---
-#pragma unroll
-  for (int l = 0; l < NRT_L; ++l) {
-    float2 f = level_gather(P.lv[l], grid, x0, x1, x2);
-    if (feat_out) reinterpret_cast<float2*>(feat_out)[l] = f;
-    fma_row32(f.x, sw + SW_W1T + (2 * l) * 32, h);
-    fma_row32(f.y, sw + SW_W1T + (2 * l + 1) * 32, h);
-  }
-  out.unc = uncert_sample(P, ug, x0, x1, x2);
-  // --- OneBlob -> layer 1 (rows 32..79) and colour layer 1 (rows 0..47) ---
-  {
-    float xs[3] = {x0, x1, x2};
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      float bins[NRT_BINS];
-      oneblob16(xs[d], bins);
-#pragma unroll
-      for (int b = 0; b < NRT_BINS; ++b) {
-        fma_row32(bins[b], sw + SW_W1T + (NRT_ENC + d * NRT_BINS + b) * 32, h);
-        if (COLOR) fma_row32(bins[b], sw + SW_W3T + (d * NRT_BINS + b) * 32, a3);
-      }
-    }
-  }
-  // --- SDF net layer 2 ---
-  float o[NRT_O];
-#pragma unroll
-  for (int i = 0; i < NRT_O; ++i) o[i] = 0.f;
-#pragma unroll
-  for (int j = 0; j < NRT_H; ++j) {
-    float v = fmaxf(h[j], 0.f);
-    const float4* r4 = reinterpret_cast<const float4*>(sw + SW_W2T + j * 16);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 w = r4[q];
-      o[4 * q + 0] = fmaf(v, w.x, o[4 * q + 0]);
-      o[4 * q + 1] = fmaf(v, w.y, o[4 * q + 1]);
-      o[4 * q + 2] = fmaf(v, w.z, o[4 * q + 2]);
-      o[4 * q + 3] = fmaf(v, w.w, o[4 * q + 3]);
-    }
-  }
-  out.sdf = o[0];
-#pragma unroll
-  for (int k = 0; k < NRT_GEO; ++k) out.geo[k] = o[1 + k];
-  if (COLOR) {
-#pragma unroll
-    for (int k = 0; k < NRT_GEO; ++k) fma_row32(o[1 + k], sw + SW_W3T + (NRT_OB + k) * 32, a3);
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < NRT_H; ++j) {
-      float v = fmaxf(a3[j], 0.f);
-      float4 w = *reinterpret_cast<const float4*>(sw + SW_W4T + j * 4);
-      c0 = fmaf(v, w.x, c0);
-      c1 = fmaf(v, w.y, c1);
-      c2 = fmaf(v, w.z, c2);
-    }
-    out.rgb[0] = c0;
-    out.rgb[1] = c1;
-    out.rgb[2] = c2;
-  } else {
-    out.rgb[0] = out.rgb[1] = out.rgb[2] = 0.f;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // depth sampling for one ray, executed by one warp (src/slam/coslam/model/scene_rep.py:158-180).

@@ -19,109 +19,10 @@
 // (calc_embedding / query_sdf / query_color_sdf), src/slam/coslam/model/decoder.py:29-41,99-116, and for the ray kernel
 // src/slam/coslam/model/scene_rep.py:150-225,66-96 with tp/model/scene_rep.py:64-84.
 #include "common.cuh"
-#include "umma.cuh"
+#include "mlp_tc.cuh"
 
-using namespace umma;
-
-// shared-memory weight block (floats): chunk-major K-major B operands; the lo pieces follow at +FW_FLOATS
-#define FW_W1 0                   // [20 K-chunks][32 rows j][4]   k: hash 0..31 | oneblob 32..79
-#define FW_W2 (FW_W1 + 80 * 32)   // [ 8][16 rows i][4]            k: h1 0..31
-#define FW_W3 (FW_W2 + 32 * 16)   // [16][32 rows j][4]            k: oneblob 0..47 | geo 48..62 | 0
-#define FW_W4 (FW_W3 + 64 * 32)   // [ 8][16 rows i][4]            rows 3..15 = 0
-#define FW_FLOATS (FW_W4 + 32 * 16)
-
-#define TC_ACC 0
-#define TC_AHI 32
-#define TC_ALO 128
-#define TA_X0 0
-#define TA_OB 32
-#define TA_GEO 80
-#define TC_COLS 256
-
+#define TC_COLS 256               // TMEM columns per CTA (two CTAs per SM)
 #define UNIT_PTS_MAX 2048         // sample points of one ray block staged in shared memory
-
-__device__ __forceinline__ void load_weights_tc(float* sw, const NrtParams& prm) {
-  float* lo = sw + FW_FLOATS;
-  for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) {
-    const int j = i / 80, k = i % 80;
-    const float v = __ldg(prm.w1 + i), h = tf32_hi(v);
-    const int o = FW_W1 + ((k >> 2) * 32 + j) * 4 + (k & 3);
-    sw[o] = h;
-    lo[o] = v - h;
-  }
-  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
-    const int r = i >> 5, k = i & 31;
-    const float v = __ldg(prm.w2 + i), h = tf32_hi(v);
-    const int o = FW_W2 + ((k >> 2) * 16 + r) * 4 + (k & 3);
-    sw[o] = h;
-    lo[o] = v - h;
-  }
-  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
-    const int j = i >> 6, k = i & 63;
-    const float v = k < 63 ? __ldg(prm.w3 + j * 63 + k) : 0.f, h = tf32_hi(v);
-    const int o = FW_W3 + ((k >> 2) * 32 + j) * 4 + (k & 3);
-    sw[o] = h;
-    lo[o] = v - h;
-  }
-  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
-    const int r = i >> 5, k = i & 31;
-    const float v = r < 3 ? __ldg(prm.w4 + r * 32 + k) : 0.f, h = tf32_hi(v);
-    const int o = FW_W4 + ((k >> 2) * 16 + r) * 4 + (k & 3);
-    sw[o] = h;
-    lo[o] = v - h;
-  }
-}
-
-struct TileCtx {
-  uint32_t tb;         // TMEM base of this CTA
-  uint32_t lane_tb;    // tb + (32*warp << 16): the lanes this warp may touch
-  uint64_t* bar;       // MMA-complete mbarrier
-  uint32_t phase;
-  uint32_t w_hi, w_lo; // shared-memory addresses of the weight blocks
-};
-
-// D[:, 0:N) = A[:, a_col : a_col+K) * W^T in three tf32 passes; issued by one thread, completion -> c.bar
-template <int K, int N>
-__device__ __forceinline__ void issue_layer(const TileCtx& c, int a_col, int w_off) {
-  constexpr uint32_t idesc = idesc_tf32(128, N, 0, 0);
-  const uint32_t d = c.tb + TC_ACC;
-  const uint32_t wh = c.w_hi + w_off * 4, wl = c.w_lo + w_off * 4;
-#pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wh, N, 2 * ks), idesc, ks > 0);
-#pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_ALO + a_col + 8 * ks, desc_kmajor(wh, N, 2 * ks), idesc, true);
-#pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wl, N, 2 * ks), idesc, true);
-  mma_commit(c.bar);
-}
-
-// all threads: publish this thread's TMEM stores, let thread 0 issue the layer, wait for the accumulator
-template <int K, int N>
-__device__ __forceinline__ void run_layer(TileCtx& c, int a_col, int w_off) {
-  tmem_st_wait();
-  tc_fence_before();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    tc_fence_after();
-    issue_layer<K, N>(c, a_col, w_off);
-  }
-  __syncwarp();
-  mbar_wait(c.bar, c.phase);
-  c.phase ^= 1u;
-  tc_fence_after();
-}
-
-// stage 16 consecutive A columns (hi and lo pieces) of this thread's row
-__device__ __forceinline__ void stage16(const TileCtx& c, int col, const float* v) {
-  float hi[16], lo[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    hi[i] = tf32_hi(v[i]);
-    lo[i] = v[i] - hi[i];
-  }
-  tmem_st16(c.lane_tb + TC_AHI + col, hi);
-  tmem_st16(c.lane_tb + TC_ALO + col, lo);
-}
 
 // One tile: every thread of the CTA calls this with its own point (inactive threads feed zeros).
 template <bool COLOR>
@@ -129,39 +30,37 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
                                             const float* __restrict__ ug, bool active, float x0, float x1, float x2,
                                             float* __restrict__ feat_out, PointOut& out) {
   // ---- encodings -> TMEM ----
+  // hash levels, four per iteration (32 independent 8-byte gathers in flight per thread); the loop is kept rolled so the
+  // tile body stays inside the instruction cache
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    float f[8];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    float f[16];
-#pragma unroll
-    for (int l = 0; l < 8; ++l) {
+    for (int l = 0; l < 4; ++l) {
       float2 v = make_float2(0.f, 0.f);
-      if (active) v = level_gather(P.lv[half * 8 + l], grid, x0, x1, x2);
+      if (active) v = level_gather(P.lv[g * 4 + l], grid, x0, x1, x2);
       f[2 * l] = v.x;
       f[2 * l + 1] = v.y;
     }
     if (feat_out) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        reinterpret_cast<float4*>(feat_out)[half * 4 + q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      reinterpret_cast<float4*>(feat_out)[g * 2] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(feat_out)[g * 2 + 1] = make_float4(f[4], f[5], f[6], f[7]);
     }
-    stage16(c, TA_X0 + 16 * half, f);
+    stage8(c, TA_X0 + 8 * g, f);
   }
-  {
-    const float xs[3] = {x0, x1, x2};
+#pragma unroll 1
+  for (int d = 0; d < 3; ++d) {
+    float bins[NRT_BINS];
+    oneblob16_fast(d == 0 ? x0 : d == 1 ? x1 : x2, bins);
+    if (!active) {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      float bins[NRT_BINS];
-      oneblob16(xs[d], bins);
-      if (!active) {
-#pragma unroll
-        for (int b = 0; b < NRT_BINS; ++b) bins[b] = 0.f;
-      }
-      stage16(c, TA_OB + 16 * d, bins);
+      for (int b = 0; b < NRT_BINS; ++b) bins[b] = 0.f;
     }
+    stage16(c, TA_OB + 16 * d, bins);
   }
   out.unc = active ? uncert_sample(P, ug, x0, x1, x2) : 0.f;
   // ---- SDF net ----
-  run_layer<80, 32>(c, TA_X0, FW_W1);
+  run_layer<80, 32>(c, TA_X0, c.w_hi + FW_W1 * 4, c.w_lo + FW_W1 * 4);
   {
     float h[32];
     tmem_ld16(c.lane_tb + TC_ACC, h);
@@ -172,7 +71,7 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
     stage16(c, TA_X0, h);
     stage16(c, TA_X0 + 16, h + 16);
   }
-  run_layer<32, 16>(c, TA_X0, FW_W2);
+  run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W2 * 4, c.w_lo + FW_W2 * 4);
   {
     float o[16];
     tmem_ld16(c.lane_tb + TC_ACC, o);
@@ -190,7 +89,7 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
   }
   if (COLOR) {
     // ---- colour net ----
-    run_layer<64, 32>(c, TA_OB, FW_W3);
+    run_layer<64, 32>(c, TA_OB, c.w_hi + FW_W3 * 4, c.w_lo + FW_W3 * 4);
     {
       float h[32];
       tmem_ld16(c.lane_tb + TC_ACC, h);
@@ -201,7 +100,7 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
       stage16(c, TA_X0, h);
       stage16(c, TA_X0 + 16, h + 16);
     }
-    run_layer<32, 16>(c, TA_X0, FW_W4);
+    run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W4 * 4, c.w_lo + FW_W4 * 4);
     {
       float r[4];
       tmem_ld4(c.lane_tb + TC_ACC, r);
@@ -217,51 +116,6 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
   // has completed, and the accumulator is next written by an MMA issued after the next run_layer() barrier.
 }
 
-struct CtaSetup {
-  float* sw;
-  uint64_t* bar;
-  uint32_t* slot;
-};
-
-// common prologue: weights -> smem, barrier init, TMEM allocation.  smem_raw: [bar 8 | slot 4 | pad | weights hi | weights lo | ...]
-__device__ __forceinline__ TileCtx cta_prologue(uint8_t* smem_raw, const NrtParams& prm, float** after_weights) {
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
-  float* sw = reinterpret_cast<float*>(smem_raw + 128);
-  const int warp = threadIdx.x >> 5;
-  if (warp == 0) {
-    if (threadIdx.x == 0) {
-      mbar_init(bar, 1);
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc<TC_COLS>(slot);
-  }
-  load_weights_tc(sw, prm);
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  TileCtx c;
-  c.tb = *slot;
-  c.lane_tb = c.tb + ((uint32_t)(32 * warp) << 16);
-  c.bar = bar;
-  c.phase = 0u;
-  c.w_hi = smem_u32(sw);
-  c.w_lo = smem_u32(sw + FW_FLOATS);
-  *after_weights = sw + 2 * FW_FLOATS;
-  return c;
-}
-
-__device__ __forceinline__ void cta_epilogue(const TileCtx& c) {
-  tc_fence_before();
-  __syncthreads();
-  if ((threadIdx.x >> 5) == 0) tmem_dealloc<TC_COLS>(c.tb);
-}
-
-#define TC_SMEM_HEADER 128
-#define TC_SMEM_WEIGHTS (TC_SMEM_HEADER + 2 * FW_FLOATS * 4)
-
 // ---------------------------------------------------------------------------------------------
 // point decode
 // ---------------------------------------------------------------------------------------------
@@ -271,7 +125,8 @@ __global__ void __launch_bounds__(128, 2) points_fwd_tc_kernel(const __grid_cons
                                                                float* __restrict__ sdf_uncert, float* __restrict__ geo) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* rest;
-  TileCtx c = cta_prologue(smem_raw, prm, &rest);
+  TileCtx c = cta_prologue<TC_COLS>(smem_raw, prm, &rest);
+  cta_prologue_finish(smem_raw, c);
   const float2* grid = reinterpret_cast<const float2*>(prm.grid);
   const int64_t n_tiles = (n + 127) / 128;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -301,7 +156,7 @@ __global__ void __launch_bounds__(128, 2) points_fwd_tc_kernel(const __grid_cons
       }
     }
   }
-  cta_epilogue(c);
+  cta_epilogue<TC_COLS>(c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -315,7 +170,8 @@ __global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_cons
                                                                int perturb, uint64_t seed, int rpu, const NrtRenderOut out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* rest;
-  TileCtx c = cta_prologue(smem_raw, prm, &rest);
+  TileCtx c = cta_prologue<TC_COLS>(smem_raw, prm, &rest);
+  cta_prologue_finish(smem_raw, c);
   const int S = P.S;
   float* s_ray = rest;
   float* s_z = s_ray + rpu * 6;
@@ -395,7 +251,7 @@ __global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_cons
     }
     __syncthreads();
   }
-  cta_epilogue(c);
+  cta_epilogue<TC_COLS>(c);
 }
 
 // ---------------------------------------------------------------------------------------------

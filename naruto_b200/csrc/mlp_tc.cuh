@@ -1,0 +1,166 @@
+// Shared pieces of the tensor-core MLP kernels (forward_tc.cu, backward_tc.cu): weight staging, the TMEM column map,
+// the three-pass tf32 layer issue and the per-CTA prologue / epilogue.
+//
+// One CTA = 128 threads = one tile of 128 points; thread t owns point t = tensor-memory lane t.  Activations are
+// staged by their owner thread into TMEM as tf32 hi/lo pieces (A operand of tcgen05.mma, A-from-TMEM form); weights are
+// the B operand in shared memory (chunk-major K-major, hi and lo copies).
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+using namespace umma;
+
+// shared-memory forward weight block (floats): chunk-major K-major B operands; the lo pieces follow at +FW_FLOATS
+#define FW_W1 0                   // [20 K-chunks][32 rows j][4]   k: hash 0..31 | oneblob 32..79
+#define FW_W2 (FW_W1 + 80 * 32)   // [ 8][16 rows i][4]            k: h1 0..31
+#define FW_W3 (FW_W2 + 32 * 16)   // [16][32 rows j][4]            k: oneblob 0..47 | geo 48..62 | 0
+#define FW_W4 (FW_W3 + 64 * 32)   // [ 8][16 rows i][4]            rows 3..15 = 0
+#define FW_FLOATS (FW_W4 + 32 * 16)
+
+// TMEM columns common to both kernels
+#define TC_ACC 0                  // [0,32)    accumulator of the current layer
+#define TC_AHI 32                 // [32,128)  A_hi: X0[32] | OneBlob[48] | geo[16]
+#define TC_ALO 128                // [128,224) A_lo: same structure, the low-order pieces
+#define TA_X0 0
+#define TA_OB 32
+#define TA_GEO 80
+
+#define TC_SMEM_HEADER 128
+#define TC_SMEM_WEIGHTS (TC_SMEM_HEADER + 2 * FW_FLOATS * 4)
+
+__device__ __forceinline__ void put_split(float* hi_blk, int o, float v) {
+  const float h = tf32_hi(v);
+  hi_blk[o] = h;
+  hi_blk[o + FW_FLOATS] = v - h;
+}
+
+__device__ __forceinline__ void load_weights_tc(float* sw, const NrtParams& prm) {
+  for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) {
+    const int j = i / 80, k = i % 80;
+    put_split(sw, FW_W1 + ((k >> 2) * 32 + j) * 4 + (k & 3), __ldg(prm.w1 + i));
+  }
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int r = i >> 5, k = i & 31;
+    put_split(sw, FW_W2 + ((k >> 2) * 16 + r) * 4 + (k & 3), __ldg(prm.w2 + i));
+  }
+  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
+    const int j = i >> 6, k = i & 63;
+    put_split(sw, FW_W3 + ((k >> 2) * 32 + j) * 4 + (k & 3), k < 63 ? __ldg(prm.w3 + j * 63 + k) : 0.f);
+  }
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int r = i >> 5, k = i & 31;
+    put_split(sw, FW_W4 + ((k >> 2) * 16 + r) * 4 + (k & 3), r < 3 ? __ldg(prm.w4 + r * 32 + k) : 0.f);
+  }
+}
+
+struct TileCtx {
+  uint32_t tb;         // TMEM base of this CTA
+  uint32_t lane_tb;    // tb + (32*warp << 16): the lanes this warp may touch
+  uint64_t* bar;       // MMA-complete mbarrier
+  uint32_t phase;
+  uint32_t w_hi, w_lo; // shared-memory addresses of the forward weight block (hi / lo)
+};
+
+// D[:, 0:N) = A[:, a_col : a_col+K) * W^T in three tf32 passes (hi*hi + lo*hi + hi*lo); one thread issues.
+// wh / wl: shared-memory byte addresses of the [K/4][N][4] hi / lo weight operand.
+template <int K, int N>
+__device__ __forceinline__ void issue_layer(const TileCtx& c, int a_col, uint32_t wh, uint32_t wl) {
+  constexpr uint32_t idesc = idesc_tf32(128, N, 0, 0);
+  const uint32_t d = c.tb + TC_ACC;
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wh, N, 2 * ks), idesc, ks > 0);
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_ALO + a_col + 8 * ks, desc_kmajor(wh, N, 2 * ks), idesc, true);
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wl, N, 2 * ks), idesc, true);
+}
+
+// all threads: make this thread's TMEM stores visible, then meet at the CTA barrier
+__device__ __forceinline__ void layer_publish() {
+  tmem_st_wait();
+  tc_fence_before();
+  __syncthreads();
+}
+// all threads: wait until the MMAs committed to c.bar have completed
+__device__ __forceinline__ void layer_wait(TileCtx& c) {
+  __syncwarp();
+  mbar_wait(c.bar, c.phase);
+  c.phase ^= 1u;
+  tc_fence_after();
+}
+
+// publish -> thread 0 issues one layer -> wait for its accumulator
+template <int K, int N>
+__device__ __forceinline__ void run_layer(TileCtx& c, int a_col, uint32_t wh, uint32_t wl) {
+  layer_publish();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    issue_layer<K, N>(c, a_col, wh, wl);
+    mma_commit(c.bar);
+  }
+  layer_wait(c);
+}
+
+// stage 16 / 8 consecutive A columns (hi and lo pieces) of this thread's row
+__device__ __forceinline__ void stage16(const TileCtx& c, int col, const float* v) {
+  float hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    hi[i] = tf32_hi(v[i]);
+    lo[i] = v[i] - hi[i];
+  }
+  tmem_st16(c.lane_tb + TC_AHI + col, hi);
+  tmem_st16(c.lane_tb + TC_ALO + col, lo);
+}
+__device__ __forceinline__ void stage8(const TileCtx& c, int col, const float* v) {
+  float hi[8], lo[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = tf32_hi(v[i]);
+    lo[i] = v[i] - hi[i];
+  }
+  tmem_st8(c.lane_tb + TC_AHI + col, hi);
+  tmem_st8(c.lane_tb + TC_ALO + col, lo);
+}
+
+// common prologue: forward weights -> smem, barrier init, TMEM allocation.
+// smem_raw: [bar 8 | slot 4 | pad to 128 | weights hi | weights lo | kernel-specific ...]
+template <int NCOLS>
+__device__ __forceinline__ TileCtx cta_prologue(uint8_t* smem_raw, const NrtParams& prm, float** after_weights) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
+  float* sw = reinterpret_cast<float*>(smem_raw + TC_SMEM_HEADER);
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<NCOLS>(slot);
+  }
+  load_weights_tc(sw, prm);
+  TileCtx c;
+  c.bar = bar;
+  c.phase = 0u;
+  c.w_hi = smem_u32(sw);
+  c.w_lo = smem_u32(sw + FW_FLOATS);
+  *after_weights = sw + 2 * FW_FLOATS;
+  return c;
+}
+// second half of the prologue, after the kernel has written its own shared-memory operands
+__device__ __forceinline__ void cta_prologue_finish(uint8_t* smem_raw, TileCtx& c) {
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tb = *reinterpret_cast<uint32_t*>(smem_raw + 8);
+  c.lane_tb = c.tb + ((uint32_t)(32 * (threadIdx.x >> 5)) << 16);
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void cta_epilogue(const TileCtx& c) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc<NCOLS>(c.tb);
+}

@@ -231,10 +231,13 @@ def test_decode_backward_vs_oracle(spec, dev):
     Pg = P.clone(requires_grad=True)
     (no.decode(x, Pg, spec) * draw).sum().backward()
     (m.query_color_sdf(x.to(dev)) * draw.to(dev)).sum().backward()
-    close(m.decoder.sdf_net.model[0].weight.grad, Pg.w1.grad, 1e-4, 'w1')
-    close(m.decoder.sdf_net.model[2].weight.grad, Pg.w2.grad, 1e-4, 'w2')
-    close(m.decoder.color_net.model[0].weight.grad, Pg.w3.grad, 1e-4, 'w3')
-    close(m.decoder.color_net.model[2].weight.grad, Pg.w4.grad, 1e-4, 'w4')
+    # MLP weight gradients: the contraction over points runs as ONE single-pass TF32 tensor-core GEMM (operands rounded to
+    # nearest, fp32 accumulate; DESIGN.md "precision"), so each product carries ~2^-11 relative rounding noise: 1e-3 of the
+    # tensor's scale.  Everything on the data path (hash-feature / grid gradients below) is 3xTF32 and held to 1e-4.
+    close(m.decoder.sdf_net.model[0].weight.grad, Pg.w1.grad, 1e-3, 'w1')
+    close(m.decoder.sdf_net.model[2].weight.grad, Pg.w2.grad, 1e-3, 'w2')
+    close(m.decoder.color_net.model[0].weight.grad, Pg.w3.grad, 1e-3, 'w3')
+    close(m.decoder.color_net.model[2].weight.grad, Pg.w4.grad, 1e-3, 'w4')
     close(m.embed_fn.params.grad, Pg.grid.grad, 1e-4, 'grid')
     close(m.uncert_grid.grad, Pg.uncert_grid.grad, 1e-4, 'uncert')
 
