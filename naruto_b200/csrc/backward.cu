@@ -96,55 +96,67 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
-// hash-table scatter: thread = (point, level), level fastest
+// hash-table scatter: thread = (point, quad of levels), quad fastest: the four threads of a point each take four
+// levels (one 32-byte slice of the point's feature gradient), so the point fetch / normalisation is amortised over 32
+// reductions per thread and each thread has 32 independent red.global in flight.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) encode_bwd_kernel(const __grid_constant__ DevPlan P, const float2* __restrict__ grid,
                                                          const PointSource src, int64_t n_pts,
-                                                         const float2* __restrict__ dfeat, float scale_all,
+                                                         const float4* __restrict__ dfeat, float scale_all,
                                                          float2* __restrict__ dgrid, float* __restrict__ dx) {
   __shared__ DevLevel s_lv[NRT_L];
   if (threadIdx.x < NRT_L) s_lv[threadIdx.x] = P.lv[threadIdx.x];
   __syncthreads();
-  int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t pt = tt >> 4;
-  int l = (int)(tt & 15);
-  if (pt >= n_pts) return;
-  const unsigned live = __activemask();     // whole half-warps leave together (16 threads per point)
+  const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t pt = tt >> 2;
+  const int q = (int)(tt & 3);
+  if (pt >= n_pts) return;                  // whole groups of four threads leave together
+  const unsigned live = __activemask();
   float x0, x1, x2;
   fetch_point(P, src, pt, x0, x1, x2);
-  float2 g = __ldg(dfeat + pt * NRT_L + l);
-  g.x *= scale_all;
-  g.y *= scale_all;
-  const DevLevel& L = s_lv[l];
-  LevelPos p = level_pos(L, x0, x1, x2);
-  float2* base = dgrid ? dgrid + L.offset : nullptr;
+  const float4 ga = __ldg(dfeat + pt * 8 + q * 2), gb = __ldg(dfeat + pt * 8 + q * 2 + 1);
+  const float gl[4][2] = {{ga.x * scale_all, ga.y * scale_all}, {ga.z * scale_all, ga.w * scale_all},
+                          {gb.x * scale_all, gb.y * scale_all}, {gb.z * scale_all, gb.w * scale_all}};
   float gx[3] = {0.f, 0.f, 0.f};
-  const bool nz = g.x != 0.f || g.y != 0.f;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t idx = level_index(L, p.g[0] + (c & 1), p.g[1] + ((c >> 1) & 1), p.g[2] + ((c >> 2) & 1));
-    if (base && nz) {
-      float w = corner_weight(p, c);
-      red_add_f2(base + idx, w * g.x, w * g.y);
+  for (int li = 0; li < 4; ++li) {
+    const DevLevel& L = s_lv[q * 4 + li];
+    const float g0 = gl[li][0], g1 = gl[li][1];
+    const bool nz = g0 != 0.f || g1 != 0.f;
+    if (!nz && !dx) continue;
+    uint32_t idx[8];
+    float w[8];
+    level_corners(L, x0, x1, x2, idx, w);
+    if (dgrid && nz) {
+      float2* base = dgrid + L.offset;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) red_add_f2(base + idx[c], w[c] * g0, w[c] * g1);
     }
     if (dx) {
       // d out/d x_d = scale * sign_d * prod_{d' != d} w_d' * value
-      float2 v = ldg_f2(grid + L.offset + idx);
-      float dotv = v.x * g.x + v.y * g.y;
-      float wx = (c & 1) ? p.f[0] : 1.0f - p.f[0], wy = (c & 2) ? p.f[1] : 1.0f - p.f[1], wz = (c & 4) ? p.f[2] : 1.0f - p.f[2];
-      gx[0] += ((c & 1) ? 1.0f : -1.0f) * wy * wz * dotv;
-      gx[1] += ((c & 2) ? 1.0f : -1.0f) * wx * wz * dotv;
-      gx[2] += ((c & 4) ? 1.0f : -1.0f) * wx * wy * dotv;
+      const LevelPos p = level_pos(L, x0, x1, x2);
+      float lx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float2 v = ldg_f2(grid + L.offset + idx[c]);
+        const float dotv = v.x * g0 + v.y * g1;
+        const float wx = (c & 1) ? p.f[0] : 1.0f - p.f[0], wy = (c & 2) ? p.f[1] : 1.0f - p.f[1], wz = (c & 4) ? p.f[2] : 1.0f - p.f[2];
+        lx[0] += ((c & 1) ? 1.0f : -1.0f) * wy * wz * dotv;
+        lx[1] += ((c & 2) ? 1.0f : -1.0f) * wx * wz * dotv;
+        lx[2] += ((c & 4) ? 1.0f : -1.0f) * wx * wy * dotv;
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) gx[d] = fmaf(lx[d], L.scale, gx[d]);
     }
   }
   if (dx) {
-    // reduce the 16 levels of this point inside the half-warp, then one store
+    // reduce the four level-quads of this point, then one store
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      float v = gx[d] * L.scale;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(live, v, o, 16);
-      if (l == 0) dx[pt * 3 + d] = v;
+      float v = gx[d];
+      v += __shfl_xor_sync(live, v, 1, 4);
+      v += __shfl_xor_sync(live, v, 2, 4);
+      if (q == 0) dx[pt * 3 + d] = v;
     }
   }
 }
@@ -171,9 +183,9 @@ int launch_composite_bwd(const NrtPlan* plan, const NrtRenderOut* rend, const fl
 int launch_encode_bwd(const NrtPlan* plan, const float* grid, const PointSource& src, int64_t n_pts, const float* dfeat,
                       float scale_all, float* dgrid, float* dx, cudaStream_t st) {
   if (n_pts == 0) return NRT_OK;
-  int64_t threads = n_pts * NRT_L;
+  int64_t threads = n_pts * 4;
   encode_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(plan->dev, (const float2*)grid, src, n_pts,
-                                                                       (const float2*)dfeat, scale_all, (float2*)dgrid, dx);
+                                                                       (const float4*)dfeat, scale_all, (float2*)dgrid, dx);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

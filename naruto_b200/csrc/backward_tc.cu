@@ -1,14 +1,15 @@
 // Tensor-core backward of the two MLPs (what autograd does between dL/d raw and dL/d hash-features / dL/d weights for
 // loss.backward() at src/slam/coslam/coslam.py:216,368 through src/slam/coslam/model/decoder.py:29-41,99-116).
 //
-// One persistent CTA per SM, 128 threads, thread t = point t of the tile = TMEM lane t.  Per tile of 128 points:
+// One persistent CTA per SM, 256 threads, thread pair (r, r+128) = point r of the tile = TMEM lane r, each thread owning
+// half of the columns of every activation / gradient (mlp_tc.cuh).  Per tile of 128 points:
 //   recompute   h1 = relu(W1 [hash|oneblob]), o = W2 h1, h3 = relu(W3 [oneblob|geo])            (3 tcgen05 layers, 3xTF32)
 //   data grads  dh3 = W4^T dc (SIMT, 96 FMA) ; dgeo = W3g^T da3 ; dh1 = W2^T do ; dfeat = W1h^T da1   (3 tcgen05 layers, 3xTF32)
 //   weight grads: every activation X = [hash|oneblob|geo|h1|h3] (160) and every upstream gradient Y = [da1|da3|do|dc] (88)
 //               is also scattered, transposed and rounded to tf32, into shared memory as K-major operands over the point
 //               index, and ONE tcgen05 GEMM  D[128 x 160] += Y^T X  (K = 128 points, 16 MMAs) accumulates all four weight
 //               gradients as sub-blocks of a TMEM-resident accumulator that lives across all tiles of the CTA:
-//                   dW1 = D[0:32, 0:80]   dW3 = D[32:64, 32:95]   dW2 = D[64:80, 96:128]   dW4 = D[80:83, 128:160]
+//                   dW1 = D[0:32, 0:80]   dW3 = D[32:64, 32:80 | 81:96]   dW2 = D[64:80, 96:128]   dW4 = D[80:83, 128:160]
 //               (the other blocks are by-products the tensor pipe computes for free); flushed once per CTA with atomics.
 // TMEM: [0,32) accumulator | [32,128) A_hi | [128,224) A_lo | [224,384) D.   Shared memory ~186 KB.
 #include "mlp_tc.cuh"
@@ -17,13 +18,13 @@
 #define TC_DW 224
 
 // backward weight block (floats), hi at +0 and lo at +BW_FLOATS
-#define BW_W3G 0                   // dgeo = da3 W3[:,48:63]:  [8 K-chunks j][16 rows g][4]   row 15 = 0
+#define BW_W3G 0                   // d o[n] = da3 W3[:,48+n-1]: [8 K-chunks j][16 rows n][4]   row 0 = 0 (the sdf slot)
 #define BW_W2T (BW_W3G + 32 * 16)  // dh1 = do W2:             [4 K-chunks i][32 rows j][4]
 #define BW_W1T (BW_W2T + 16 * 32)  // dfeat = da1 W1[:, :32]:  [8 K-chunks j][32 rows f][4]
 #define BW_FLOATS (BW_W1T + 32 * 32)
 
 // transposed operands of the weight-gradient GEMM: buf[32 chunks of 4 points][R rows][4 points], R = 1 (mod 8)
-#define XT_ROWS 161                // hash 0..31 | oneblob 32..79 | geo 80..95 | h1 96..127 | h3 128..159
+#define XT_ROWS 161                // hash 0..31 | oneblob 32..79 | o = [sdf, geo] 80..95 | h1 96..127 | h3 128..159
 #define YT_ROWS 89                 // da1 0..31 | da3 32..63 | do 64..79 | dc 80..82 | zero 83..88
 #define XR_HASH 0
 #define XR_OB 32
@@ -43,10 +44,11 @@ __device__ __forceinline__ void put_split_bw(float* blk, int o, float v) {
   blk[o + BW_FLOATS] = v - h;
 }
 
-__global__ void __launch_bounds__(128, 1) decode_bwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
-                                                               const PointSource src, int64_t n_pts,
-                                                               const float* __restrict__ feat, const float* __restrict__ draw,
-                                                               float* __restrict__ dfeat, const NrtGrads grads) {
+__global__ void __launch_bounds__(TC_THREADS, 1) decode_bwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
+                                                                      const PointSource src, int64_t n_pts,
+                                                                      const float* __restrict__ feat,
+                                                                      const float* __restrict__ draw, float* __restrict__ dfeat,
+                                                                      const NrtGrads grads) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* rest;
   TileCtx c = cta_prologue<BT_COLS>(smem_raw, prm, &rest);
@@ -54,32 +56,32 @@ __global__ void __launch_bounds__(128, 1) decode_bwd_tc_kernel(const __grid_cons
   float* w4s = bw + 2 * BW_FLOATS;        // w4 as stored [3][32] (+ pad)
   float* xt = w4s + 128;
   float* yt = xt + XT_FLOATS;
-  const int t = threadIdx.x;
-  for (int i = t; i < 16 * 32; i += 128) {         // W3G[g][j] = w3[j][48+g]
-    const int g = i >> 5, j = i & 31;
-    put_split_bw(bw, BW_W3G + ((j >> 2) * 16 + g) * 4 + (j & 3), g < NRT_GEO ? __ldg(prm.w3 + j * 63 + NRT_OB + g) : 0.f);
+  const int t = threadIdx.x, half = tc_half(), row = tc_row();
+  for (int i = t; i < 16 * 32; i += TC_THREADS) {  // W3G[n][j] = w3[j][48 + n - 1] (n >= 1): output column n is d o[n]
+    const int n = i >> 5, j = i & 31;
+    put_split_bw(bw, BW_W3G + ((j >> 2) * 16 + n) * 4 + (j & 3), n >= 1 ? __ldg(prm.w3 + j * 63 + NRT_OB + n - 1) : 0.f);
   }
-  for (int i = t; i < 32 * 16; i += 128) {         // W2T[j][i] = w2[i][j]
+  for (int i = t; i < 32 * 16; i += TC_THREADS) {  // W2T[j][i] = w2[i][j]
     const int j = i >> 4, ii = i & 15;
     put_split_bw(bw, BW_W2T + ((ii >> 2) * 32 + j) * 4 + (ii & 3), __ldg(prm.w2 + ii * 32 + j));
   }
-  for (int i = t; i < 32 * 32; i += 128) {         // W1T[f][j] = w1[j][f]
+  for (int i = t; i < 32 * 32; i += TC_THREADS) {  // W1T[f][j] = w1[j][f]
     const int f = i >> 5, j = i & 31;
     put_split_bw(bw, BW_W1T + ((j >> 2) * 32 + f) * 4 + (j & 3), __ldg(prm.w1 + j * 80 + f));
   }
-  for (int i = t; i < 128; i += 128) w4s[i] = i < 96 ? __ldg(prm.w4 + i) : 0.f;
-  for (int i = t; i < YT_FLOATS; i += 128) yt[i] = 0.f;      // rows 83.. and the slack stay zero for the whole kernel
+  for (int i = t; i < 128; i += TC_THREADS) w4s[i] = i < 96 ? __ldg(prm.w4 + i) : 0.f;
+  for (int i = t; i < YT_FLOATS; i += TC_THREADS) yt[i] = 0.f;   // rows 83.. and the slack stay zero for the whole kernel
   cta_prologue_finish(smem_raw, c);
   const uint32_t bw_hi = smem_u32(bw), bw_lo = smem_u32(bw + BW_FLOATS);
   const uint32_t xt_s = smem_u32(xt), yt_s = smem_u32(yt);
-  // this thread's column of the transposed operands
-  float* xcol = xt + (t >> 2) * (XT_ROWS * 4) + (t & 3);
-  float* ycol = yt + (t >> 2) * (YT_ROWS * 4) + (t & 3);
+  // this row's column of the transposed operands
+  float* xcol = xt + (row >> 2) * (XT_ROWS * 4) + (row & 3);
+  float* ycol = yt + (row >> 2) * (YT_ROWS * 4) + (row & 3);
 
   const int64_t n_tiles = (n_pts + 127) / 128;
   bool first_tile = true;
   for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
-    const int64_t pt = tl * 128 + t;
+    const int64_t pt = tl * 128 + row;
     const bool active = pt < n_pts;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     float dc[3] = {0.f, 0.f, 0.f}, dsdf = 0.f, du = 0.f;
@@ -89,12 +91,11 @@ __global__ void __launch_bounds__(128, 1) decode_bwd_tc_kernel(const __grid_cons
       dc[0] = __ldg(g);
       dc[1] = __ldg(g + 1);
       dc[2] = __ldg(g + 2);
-      dsdf = __ldg(g + 3);
-      du = __ldg(g + 4);
+      if (half == 0) dsdf = __ldg(g + 3);
+      else du = __ldg(g + 4);
     }
     // ---- saved hash features + OneBlob -> A operand (TMEM) and X^T (smem) ----
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       float f[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(128, 1) decode_bwd_tc_kernel(const __grid_cons
       tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
     }
 #pragma unroll 1
-    for (int d = 0; d < 3; ++d) {
+    for (int d = 2 * half; d < 2 + half; ++d) {
       float bins[NRT_BINS];
       oneblob16_fast(d == 0 ? x0 : d == 1 ? x1 : x2, bins);
       float hi[16], lo[16];
@@ -131,111 +132,98 @@ __global__ void __launch_bounds__(128, 1) decode_bwd_tc_kernel(const __grid_cons
     }
     // ---- recompute layer 1 ----
     run_layer<80, 32>(c, TA_X0, c.w_hi + FW_W1 * 4, c.w_lo + FW_W1 * 4);
-    unsigned m1 = 0u;
+    unsigned m1 = 0u;                 // ReLU mask of this half's 16 hidden units
     {
-      float h[32];
-      tmem_ld16(c.lane_tb + TC_ACC, h);
-      tmem_ld16(c.lane_tb + TC_ACC + 16, h + 16);
-      tmem_ld_wait();
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int j = 16 * half + i;
-          const float v = fmaxf(h[j], 0.f);
-          if (v > 0.f) m1 |= 1u << j;
-          hi[i] = tf32_hi(v);
-          lo[i] = v - hi[i];
-          xcol[(XR_H1 + j) * 4] = hi[i];
-        }
-        tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
-        tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
-      }
-    }
-    // ---- recompute layer 2 ----
-    run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W2 * 4, c.w_lo + FW_W2 * 4);
-    {
-      float o[16];
-      tmem_ld16(c.lane_tb + TC_ACC, o);
+      float h[16];
+      tmem_ld16(c.lane_tb + TC_ACC + 16 * half, h);
       tmem_ld_wait();
       float hi[16], lo[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float v = k < NRT_GEO ? o[1 + k] : 0.f;
-        hi[k] = tf32_hi(v);
-        lo[k] = v - hi[k];
-        xcol[(XR_GEO + k) * 4] = hi[k];
+      for (int i = 0; i < 16; ++i) {
+        const float v = fmaxf(h[i], 0.f);
+        if (v > 0.f) m1 |= 1u << i;
+        hi[i] = tf32_hi(v);
+        lo[i] = v - hi[i];
+        xcol[(XR_H1 + 16 * half + i) * 4] = hi[i];
       }
-      tmem_st16(c.lane_tb + TC_AHI + TA_GEO, hi);
-      tmem_st16(c.lane_tb + TC_ALO + TA_GEO, lo);
+      tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
+      tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
+    }
+    // ---- recompute layer 2: o = [sdf, geo] ----
+    run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W2 * 4, c.w_lo + FW_W2 * 4);
+    {
+      float o[8];
+      tmem_ld8(c.lane_tb + TC_ACC + 8 * half, o);
+      tmem_ld_wait();
+      float hi[8], lo[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        hi[k] = tf32_hi(o[k]);
+        lo[k] = o[k] - hi[k];
+        xcol[(XR_GEO + 8 * half + k) * 4] = hi[k];
+      }
+      tmem_st8(c.lane_tb + TC_AHI + TA_GEO + 8 * half, hi);
+      tmem_st8(c.lane_tb + TC_ALO + TA_GEO + 8 * half, lo);
     }
     // ---- recompute colour layer 1 ----
     run_layer<64, 32>(c, TA_OB, c.w_hi + FW_W3 * 4, c.w_lo + FW_W3 * 4);
     {
       // h3 = relu(a3); dh3 = W4^T dc; da3 = dh3 * relu'
-      float a3[32];
-      tmem_ld16(c.lane_tb + TC_ACC, a3);
-      tmem_ld16(c.lane_tb + TC_ACC + 16, a3 + 16);
+      float a3[16];
+      tmem_ld16(c.lane_tb + TC_ACC + 16 * half, a3);
       tmem_ld_wait();
+      if (half == 0) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) ycol[(YR_DC + k) * 4] = tf32_hi(dc[k]);
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int j = 16 * half + i;
-          const float hv = fmaxf(a3[j], 0.f);
-          xcol[(XR_H3 + j) * 4] = tf32_hi(hv);
-          const float d = dc[0] * w4s[j] + dc[1] * w4s[32 + j] + dc[2] * w4s[64 + j];
-          const float v = hv > 0.f ? d : 0.f;
-          hi[i] = tf32_hi(v);
-          lo[i] = v - hi[i];
-          ycol[(YR_DA3 + j) * 4] = hi[i];
-        }
-        tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
-        tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
+        for (int k = 0; k < 3; ++k) ycol[(YR_DC + k) * 4] = tf32_hi(dc[k]);
       }
-    }
-    // ---- dgeo = da3 W3[:, 48:63] ----
-    run_layer<32, 16>(c, TA_X0, bw_hi + BW_W3G * 4, bw_lo + BW_W3G * 4);
-    {
-      float dg[16];
-      tmem_ld16(c.lane_tb + TC_ACC, dg);
-      tmem_ld_wait();
       float hi[16], lo[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float v = i == 0 ? dsdf : dg[i - 1];       // do = [dsdf, dgeo[0..14]]
+        const int j = 16 * half + i;
+        const float hv = fmaxf(a3[i], 0.f);
+        xcol[(XR_H3 + j) * 4] = tf32_hi(hv);
+        const float d = dc[0] * w4s[j] + dc[1] * w4s[32 + j] + dc[2] * w4s[64 + j];
+        const float v = hv > 0.f ? d : 0.f;
         hi[i] = tf32_hi(v);
         lo[i] = v - hi[i];
-        ycol[(YR_DO + i) * 4] = hi[i];
+        ycol[(YR_DA3 + j) * 4] = hi[i];
       }
-      tmem_st16(c.lane_tb + TC_AHI + TA_GEO, hi);
-      tmem_st16(c.lane_tb + TC_ALO + TA_GEO, lo);
+      tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
+      tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
+    }
+    // ---- d o = [dsdf, da3 W3[:, 48:63]] ----
+    run_layer<32, 16>(c, TA_X0, bw_hi + BW_W3G * 4, bw_lo + BW_W3G * 4);
+    {
+      float dg[8];
+      tmem_ld8(c.lane_tb + TC_ACC + 8 * half, dg);
+      tmem_ld_wait();
+      if (half == 0) dg[0] = dsdf;                      // column 0 of the accumulator is identically zero
+      float hi[8], lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        hi[i] = tf32_hi(dg[i]);
+        lo[i] = dg[i] - hi[i];
+        ycol[(YR_DO + 8 * half + i) * 4] = hi[i];
+      }
+      tmem_st8(c.lane_tb + TC_AHI + TA_GEO + 8 * half, hi);
+      tmem_st8(c.lane_tb + TC_ALO + TA_GEO + 8 * half, lo);
     }
     // ---- dh1 = do W2 ----
     run_layer<16, 32>(c, TA_GEO, bw_hi + BW_W2T * 4, bw_lo + BW_W2T * 4);
     {
-      float dh[32];
-      tmem_ld16(c.lane_tb + TC_ACC, dh);
-      tmem_ld16(c.lane_tb + TC_ACC + 16, dh + 16);
+      float dh[16];
+      tmem_ld16(c.lane_tb + TC_ACC + 16 * half, dh);
       tmem_ld_wait();
+      float hi[16], lo[16];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int j = 16 * half + i;
-          const float v = (m1 >> j) & 1u ? dh[j] : 0.f;
-          hi[i] = tf32_hi(v);
-          lo[i] = v - hi[i];
-          ycol[(YR_DA1 + j) * 4] = hi[i];
-        }
-        tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
-        tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
+      for (int i = 0; i < 16; ++i) {
+        const float v = (m1 >> i) & 1u ? dh[i] : 0.f;
+        hi[i] = tf32_hi(v);
+        lo[i] = v - hi[i];
+        ycol[(YR_DA1 + 16 * half + i) * 4] = hi[i];
       }
+      tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
+      tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
     }
     // ---- dfeat = da1 W1[:, :32]  and the weight-gradient GEMM D += Y^T X over this tile's 128 points ----
     fence_async_smem();            // X^T / Y^T were written with generic st.shared; the MMA reads them through the async proxy
@@ -252,18 +240,17 @@ __global__ void __launch_bounds__(128, 1) decode_bwd_tc_kernel(const __grid_cons
     first_tile = false;
     layer_wait(c);
     {
-      float df[32];
-      tmem_ld16(c.lane_tb + TC_ACC, df);
-      tmem_ld16(c.lane_tb + TC_ACC + 16, df + 16);
+      float df[16];
+      tmem_ld16(c.lane_tb + TC_ACC + 16 * half, df);
       tmem_ld_wait();
       if (active && dfeat) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          reinterpret_cast<float4*>(dfeat + pt * NRT_ENC)[q] = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(dfeat + pt * NRT_ENC + 16 * half)[q] = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
       }
     }
     // uncertainty grid: raw[...,4] is the trilinear sample itself
-    if (active && grads.uncert && du != 0.f) {
+    if (half == 1 && active && grads.uncert && du != 0.f) {
       UncertPos up = uncert_pos(P, x0, x1, x2);
 #pragma unroll
       for (int cnr = 0; cnr < 8; ++cnr) {
@@ -273,26 +260,29 @@ __global__ void __launch_bounds__(128, 1) decode_bwd_tc_kernel(const __grid_cons
       }
     }
   }
-  // ---- flush the weight gradients: thread t holds row t of D ----
+  // ---- flush the weight gradients: the thread pair of row r holds row r of D, half 0 columns 0..79, half 1 80..159 ----
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (!first_tile) {
-    for (int cb = 0; cb < 160; cb += 16) {
+    for (int cb = 80 * half; cb < 80 * half + 80; cb += 16) {
       float v[16];
       tmem_ld16(c.lane_tb + TC_DW + cb, v);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int col = cb + i;
-        if (t < 32) {
-          if (col < 80 && grads.w1) atomicAdd(grads.w1 + t * 80 + col, v[i]);
-        } else if (t < 64) {
-          if (col >= 32 && col < 95 && grads.w3) atomicAdd(grads.w3 + (t - 32) * 63 + (col - 32), v[i]);
-        } else if (t < 80) {
-          if (col >= 96 && col < 128 && grads.w2) atomicAdd(grads.w2 + (t - 64) * 32 + (col - 96), v[i]);
-        } else if (t < 83) {
-          if (col >= 128 && grads.w4) atomicAdd(grads.w4 + (t - 80) * 32 + (col - 128), v[i]);
+        if (row < 32) {                       // dW1[j][k], k = hash 0..31 | oneblob 32..79
+          if (col < 80 && grads.w1) atomicAdd(grads.w1 + row * 80 + col, v[i]);
+        } else if (row < 64) {                // dW3[j][kk], kk = oneblob 0..47 (cols 32..79) | geo 48..62 (cols 81..95)
+          if (grads.w3) {
+            if (col >= 32 && col < 80) atomicAdd(grads.w3 + (row - 32) * 63 + (col - 32), v[i]);
+            else if (col >= 81 && col < 96) atomicAdd(grads.w3 + (row - 32) * 63 + (col - 33), v[i]);
+          }
+        } else if (row < 80) {                // dW2[i][j]
+          if (col >= 96 && col < 128 && grads.w2) atomicAdd(grads.w2 + (row - 64) * 32 + (col - 96), v[i]);
+        } else if (row < 83) {                // dW4[i][j]
+          if (col >= 128 && grads.w4) atomicAdd(grads.w4 + (row - 80) * 32 + (col - 128), v[i]);
         }
       }
     }
@@ -315,7 +305,7 @@ int launch_decode_bwd(const NrtPlan* plan, const NrtParams* prm, const PointSour
   }
   const int64_t tiles = (n_pts + 127) / 128;
   const int blocks = (int)(tiles < plan->sm_count ? tiles : plan->sm_count);
-  decode_bwd_tc_kernel<<<blocks, 128, smem, st>>>(plan->dev, *prm, src, n_pts, feat, draw, dfeat, *grads);
+  decode_bwd_tc_kernel<<<blocks, TC_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, draw, dfeat, *grads);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

@@ -27,6 +27,8 @@ struct DevLevel {
   uint32_t offset;    // first entry of this level in the flat table
   uint32_t hashed;    // 1: coherent prime hash, 0: dense stride walk
   uint32_t res2;      // res*res (mod 2^32)
+  uint32_t magic;     // floor(2^32 / size): umulhi(v, magic) is floor(v/size) or one less, for any 32-bit v
+  uint32_t pad;
 };
 
 struct DevPlan {
@@ -115,18 +117,20 @@ __device__ __forceinline__ LevelPos level_pos(const DevLevel& L, float x0, float
   return p;
 }
 
+// v mod L.size for any 32-bit v without a hardware divide: q = umulhi(v, floor(2^32/size)) is floor(v/size) or one
+// less, so the remainder lands in [0, 2*size) and one conditional subtract finishes it
+__device__ __forceinline__ uint32_t mod_size(const DevLevel& L, uint32_t v) {
+  uint32_t r = v - __umulhi(v, L.magic) * L.size;
+  return r >= L.size ? r - L.size : r;
+}
+
 __device__ __forceinline__ uint32_t level_index(const DevLevel& L, uint32_t cx, uint32_t cy, uint32_t cz) {
   if (L.hashed) {
     uint32_t h = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
     return h & (L.size - 1u);            // hashed levels always hold exactly 2^T entries
   }
-  uint32_t idx = cx + cy * L.res + cz * L.res2;
-  // in-bound points give idx < 2*size (vertex coordinate <= res); the full modulo is the rare path
-  if (idx >= L.size) {
-    idx -= L.size;
-    if (idx >= L.size) idx %= L.size;
-  }
-  return idx;
+  // dense stride walk in wrapping uint32 arithmetic (points outside the bound give "negative" coordinates), then % size
+  return mod_size(L, cx + cy * L.res + cz * L.res2);
 }
 
 // trilinear weight of corner c (bit d of c selects the +1 vertex along dim d), multiplied in dim order
@@ -137,23 +141,47 @@ __device__ __forceinline__ float corner_weight(const LevelPos& p, int c) {
   return w;
 }
 
+// all eight corner entries and weights of one level; one (warp-uniform) branch per level, none per corner
+__device__ __forceinline__ void level_corners(const DevLevel& L, float x0, float x1, float x2, uint32_t* __restrict__ idx,
+                                              float* __restrict__ w) {
+  const LevelPos p = level_pos(L, x0, x1, x2);
+  const float wx[2] = {1.0f - p.f[0], p.f[0]}, wy[2] = {1.0f - p.f[1], p.f[1]}, wz[2] = {1.0f - p.f[2], p.f[2]};
+  float wxy[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) wxy[c] = wx[c & 1] * wy[c >> 1];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) w[c] = wxy[c & 3] * wz[c >> 2];
+  if (L.hashed) {
+    const uint32_t hy0 = p.g[1] * 2654435761u, hz0 = p.g[2] * 805459861u;
+    const uint32_t hy[2] = {hy0, hy0 + 2654435761u}, hz[2] = {hz0, hz0 + 805459861u};
+    const uint32_t m = L.size - 1u;
+    uint32_t hyz[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) hyz[c] = hy[c & 1] ^ hz[c >> 1];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) idx[c] = ((p.g[0] + (c & 1)) ^ hyz[c >> 1]) & m;
+  } else {
+    const uint32_t base = p.g[0] + p.g[1] * L.res + p.g[2] * L.res2;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) idx[c] = mod_size(L, base + (c & 1) + ((c >> 1) & 1) * L.res + (c >> 2) * L.res2);
+  }
+}
+
 // gathers one level: returns the two interpolated features
 __device__ __forceinline__ float2 level_gather(const DevLevel& L, const float2* __restrict__ grid, float x0, float x1,
                                                float x2) {
-  LevelPos p = level_pos(L, x0, x1, x2);
+  uint32_t idx[8];
+  float w[8];
+  level_corners(L, x0, x1, x2, idx, w);
   const float2* base = grid + L.offset;
   float2 v[8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t idx = level_index(L, p.g[0] + (c & 1), p.g[1] + ((c >> 1) & 1), p.g[2] + ((c >> 2) & 1));
-    v[c] = ldg_f2(base + idx);
-  }
+  for (int c = 0; c < 8; ++c) v[c] = ldg_f2(base + idx[c]);
   float2 r = make_float2(0.f, 0.f);
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    float w = corner_weight(p, c);
-    r.x = fmaf(w, v[c].x, r.x);
-    r.y = fmaf(w, v[c].y, r.y);
+    r.x = fmaf(w[c], v[c].x, r.x);
+    r.y = fmaf(w[c], v[c].y, r.y);
   }
   return r;
 }
@@ -269,10 +297,9 @@ __device__ __forceinline__ float normalise1(const DevPlan& P, int d, float p) {
 // per-point decode result (the MLPs themselves run on the tensor cores: mlp_tc.cuh / forward_tc.cu)
 // ---------------------------------------------------------------------------------------------
 struct PointOut {
-  float rgb[3];     // colour logits
-  float sdf;
-  float unc;        // raw uncertainty sample
-  float geo[NRT_GEO];
+  float rgb[3];     // colour logits (half 0)
+  float o8[8];      // this half's slice of the SDF-net output o[16] = [sdf, geo[15]]
+  float unc;        // raw uncertainty sample (half 1)
 };
 
 // ---------------------------------------------------------------------------------------------

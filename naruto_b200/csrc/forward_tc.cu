@@ -1,6 +1,7 @@
 // Tensor-core forward path: point decode (query_sdf / query_color_sdf) and the fused render_rays kernel.
 //
-// One CTA = 128 threads = one tile of 128 sample points; thread t owns point t = tensor-memory lane t.
+// One CTA = 256 threads = one tile of 128 sample points; the thread pair (r, r+128) owns point r = tensor-memory lane r,
+// each thread taking half of the hash levels / OneBlob dims / accumulator columns (mlp_tc.cuh).
 //   SIMT part (per thread): ray march -> normalise -> 16-level hash gather (+ uncertainty trilerp) -> OneBlob;
 //                           the encoded row is split into tf32 hi/lo pieces and staged straight into TMEM (tcgen05.st).
 //   tcgen05 part (one elected thread issues): the four bias-free layers as A[tmem] x B[smem] tf32 MMAs with M=128,
@@ -24,16 +25,21 @@
 #define TC_COLS 256               // TMEM columns per CTA (two CTAs per SM)
 #define UNIT_PTS_MAX 2048         // sample points of one ray block staged in shared memory
 
-// One tile: every thread of the CTA calls this with its own point (inactive threads feed zeros).
+// One tile: every thread of the CTA calls this with the point of its row (both threads of a pair pass the same point;
+// inactive rows feed zeros).  Half 0 (threads 0..127) gathers level groups 0 and 2, OneBlob dims 0 and 1, and owns the
+// low half of every accumulator (incl. sdf and the rgb logits); half 1 gathers groups 1 and 3, OneBlob dim 2, samples the
+// uncertainty grid and owns the high halves.  Outputs land in `out` of the half that computed them.
 template <bool COLOR>
 __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const float2* __restrict__ grid,
                                             const float* __restrict__ ug, bool active, float x0, float x1, float x2,
                                             float* __restrict__ feat_out, PointOut& out) {
+  const int half = tc_half();
   // ---- encodings -> TMEM ----
-  // hash levels, four per iteration (32 independent 8-byte gathers in flight per thread); the loop is kept rolled so the
-  // tile body stays inside the instruction cache
+  // four hash levels per iteration (32 independent 8-byte gathers in flight per thread); rolled loops keep the tile body
+  // inside the instruction cache
 #pragma unroll 1
-  for (int g = 0; g < 4; ++g) {
+  for (int gi = 0; gi < 2; ++gi) {
+    const int g = 2 * gi + half;
     float f[8];
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
@@ -49,7 +55,7 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
     stage8(c, TA_X0 + 8 * g, f);
   }
 #pragma unroll 1
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 2 * half; d < 2 + half; ++d) {
     float bins[NRT_BINS];
     oneblob16_fast(d == 0 ? x0 : d == 1 ? x1 : x2, bins);
     if (!active) {
@@ -58,50 +64,36 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
     }
     stage16(c, TA_OB + 16 * d, bins);
   }
-  out.unc = active ? uncert_sample(P, ug, x0, x1, x2) : 0.f;
+  out.unc = (half == 1 && active) ? uncert_sample(P, ug, x0, x1, x2) : 0.f;
   // ---- SDF net ----
   run_layer<80, 32>(c, TA_X0, c.w_hi + FW_W1 * 4, c.w_lo + FW_W1 * 4);
   {
-    float h[32];
-    tmem_ld16(c.lane_tb + TC_ACC, h);
-    tmem_ld16(c.lane_tb + TC_ACC + 16, h + 16);
+    float h[16];
+    tmem_ld16(c.lane_tb + TC_ACC + 16 * half, h);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
-    stage16(c, TA_X0, h);
-    stage16(c, TA_X0 + 16, h + 16);
+    for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+    stage16(c, TA_X0 + 16 * half, h);
   }
   run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W2 * 4, c.w_lo + FW_W2 * 4);
   {
-    float o[16];
-    tmem_ld16(c.lane_tb + TC_ACC, o);
+    tmem_ld8(c.lane_tb + TC_ACC + 8 * half, out.o8);      // o[0] = sdf, o[1..15] = geo
     tmem_ld_wait();
-    out.sdf = o[0];
-#pragma unroll
-    for (int k = 0; k < NRT_GEO; ++k) out.geo[k] = o[1 + k];
-    if (COLOR) {
-      float g[16];
-#pragma unroll
-      for (int k = 0; k < NRT_GEO; ++k) g[k] = o[1 + k];
-      g[15] = 0.f;
-      stage16(c, TA_GEO, g);
-    }
+    if (COLOR) stage8(c, TA_GEO + 8 * half, out.o8);
   }
   if (COLOR) {
     // ---- colour net ----
     run_layer<64, 32>(c, TA_OB, c.w_hi + FW_W3 * 4, c.w_lo + FW_W3 * 4);
     {
-      float h[32];
-      tmem_ld16(c.lane_tb + TC_ACC, h);
-      tmem_ld16(c.lane_tb + TC_ACC + 16, h + 16);
+      float h[16];
+      tmem_ld16(c.lane_tb + TC_ACC + 16 * half, h);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) h[j] = fmaxf(h[j], 0.f);
-      stage16(c, TA_X0, h);
-      stage16(c, TA_X0 + 16, h + 16);
+      for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+      stage16(c, TA_X0 + 16 * half, h);
     }
     run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W4 * 4, c.w_lo + FW_W4 * 4);
-    {
+    if (half == 0) {
       float r[4];
       tmem_ld4(c.lane_tb + TC_ACC, r);
       tmem_ld_wait();
@@ -120,17 +112,19 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
 // point decode
 // ---------------------------------------------------------------------------------------------
 template <bool COLOR>
-__global__ void __launch_bounds__(128, 2) points_fwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
-                                                               const float* __restrict__ x, int64_t n, float* __restrict__ raw,
-                                                               float* __restrict__ sdf_uncert, float* __restrict__ geo) {
+__global__ void __launch_bounds__(TC_THREADS, 2) points_fwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
+                                                                      const float* __restrict__ x, int64_t n,
+                                                                      float* __restrict__ raw, float* __restrict__ sdf_uncert,
+                                                                      float* __restrict__ geo) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* rest;
   TileCtx c = cta_prologue<TC_COLS>(smem_raw, prm, &rest);
   cta_prologue_finish(smem_raw, c);
   const float2* grid = reinterpret_cast<const float2*>(prm.grid);
+  const int half = tc_half();
   const int64_t n_tiles = (n + 127) / 128;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t pt = tile * 128 + threadIdx.x;
+    const int64_t pt = tile * 128 + tc_row();
     const bool active = pt < n;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     if (active) {
@@ -141,18 +135,26 @@ __global__ void __launch_bounds__(128, 2) points_fwd_tc_kernel(const __grid_cons
     PointOut o;
     decode_tile<COLOR>(P, c, grid, prm.uncert, active, x0, x1, x2, nullptr, o);
     if (active) {
-      if (raw) {
-        float* r = raw + pt * 5;
-        r[0] = o.rgb[0];
-        r[1] = o.rgb[1];
-        r[2] = o.rgb[2];
-        r[3] = o.sdf;
-        r[4] = o.unc;
-      }
-      if (sdf_uncert) reinterpret_cast<float2*>(sdf_uncert)[pt] = make_float2(o.sdf, o.unc);
-      if (geo) {
+      if (half == 0) {
+        if (raw) {
+          float* r = raw + pt * 5;
+          r[0] = o.rgb[0];
+          r[1] = o.rgb[1];
+          r[2] = o.rgb[2];
+          r[3] = o.o8[0];
+        }
+        if (sdf_uncert) sdf_uncert[pt * 2] = o.o8[0];
+        if (geo) {
 #pragma unroll
-        for (int k = 0; k < NRT_GEO; ++k) geo[pt * NRT_GEO + k] = o.geo[k];
+          for (int k = 0; k < 7; ++k) geo[pt * NRT_GEO + k] = o.o8[1 + k];
+        }
+      } else {
+        if (raw) raw[pt * 5 + 4] = o.unc;
+        if (sdf_uncert) sdf_uncert[pt * 2 + 1] = o.unc;
+        if (geo) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) geo[pt * NRT_GEO + 7 + k] = o.o8[k];
+        }
       }
     }
   }
@@ -163,11 +165,12 @@ __global__ void __launch_bounds__(128, 2) points_fwd_tc_kernel(const __grid_cons
 // fused render_rays: a CTA takes blocks of `rpu` consecutive rays (<= UNIT_PTS_MAX sample points);
 // smem after the weights: [ray o,d: rpu*6 | z: rpu*S | raw: rpu*S*5]
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
-                                                               const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                               const float* __restrict__ target_d, int64_t n_rays,
-                                                               const float* __restrict__ z_in, const float* __restrict__ u,
-                                                               int perturb, uint64_t seed, int rpu, const NrtRenderOut out) {
+__global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
+                                                                      const float* __restrict__ rays_o,
+                                                                      const float* __restrict__ rays_d,
+                                                                      const float* __restrict__ target_d, int64_t n_rays,
+                                                                      const float* __restrict__ z_in, const float* __restrict__ u,
+                                                                      int perturb, uint64_t seed, int rpu, const NrtRenderOut out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* rest;
   TileCtx c = cta_prologue<TC_COLS>(smem_raw, prm, &rest);
@@ -177,7 +180,8 @@ __global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_cons
   float* s_z = s_ray + rpu * 6;
   float* s_raw = s_z + rpu * S;
   const float2* grid = reinterpret_cast<const float2*>(prm.grid);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = tc_half();
+  constexpr int kWarps = TC_THREADS / 32;
   const int64_t n_units = (n_rays + rpu - 1) / rpu;
 
   for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -185,11 +189,11 @@ __global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_cons
     const int nr = (int)min((int64_t)rpu, n_rays - r0);
     const int npts = nr * S;
     // ---- stage the rays and their depth samples ----
-    for (int i = threadIdx.x; i < nr * 6; i += 128) {
+    for (int i = threadIdx.x; i < nr * 6; i += TC_THREADS) {
       const int rl = i / 6, k = i - rl * 6;
       s_ray[i] = k < 3 ? __ldg(rays_o + (r0 + rl) * 3 + k) : __ldg(rays_d + (r0 + rl) * 3 + k - 3);
     }
-    for (int rl = warp; rl < nr; rl += 4) {
+    for (int rl = warp; rl < nr; rl += kWarps) {
       const int64_t ray = r0 + rl;
       float* z = s_z + rl * S;
       if (z_in) {
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_cons
     __syncthreads();
     // ---- decode tile by tile ----
     for (int t0 = 0; t0 < npts; t0 += 128) {
-      const int pl = t0 + threadIdx.x;
+      const int pl = t0 + tc_row();
       const bool active = pl < npts;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f;
       if (active) {
@@ -218,16 +222,19 @@ __global__ void __launch_bounds__(128, 2) render_fwd_tc_kernel(const __grid_cons
                         (out.feat && active) ? out.feat + (r0 * S + pl) * NRT_ENC : nullptr, po);
       if (active) {
         float* r = s_raw + pl * 5;
-        r[0] = po.rgb[0];
-        r[1] = po.rgb[1];
-        r[2] = po.rgb[2];
-        r[3] = po.sdf;
-        r[4] = po.unc;
+        if (half == 0) {
+          r[0] = po.rgb[0];
+          r[1] = po.rgb[1];
+          r[2] = po.rgb[2];
+          r[3] = po.o8[0];
+        } else {
+          r[4] = po.unc;
+        }
       }
     }
     __syncthreads();
     // ---- integrate along each ray ----
-    for (int rl = warp; rl < nr; rl += 4) {
+    for (int rl = warp; rl < nr; rl += kWarps) {
       const int64_t ray = r0 + rl;
       const float* z = s_z + rl * S;
       const float* raw = s_raw + rl * S * 5;
@@ -273,9 +280,9 @@ int launch_decode_fwd(const NrtPlan* plan, const NrtParams* prm, const float* x,
   const int64_t tiles = (n + 127) / 128;
   const int blocks = (int)(tiles < 2 * plan->sm_count ? tiles : 2 * plan->sm_count);
   if (with_color)
-    points_fwd_tc_kernel<true><<<blocks, 128, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
+    points_fwd_tc_kernel<true><<<blocks, TC_THREADS, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
   else
-    points_fwd_tc_kernel<false><<<blocks, 128, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
+    points_fwd_tc_kernel<false><<<blocks, TC_THREADS, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }
@@ -300,7 +307,7 @@ int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* ra
     attr_set = true;
   }
   const int blocks = (int)(units < slots ? units : slots);
-  render_fwd_tc_kernel<<<blocks, 128, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed,
+  render_fwd_tc_kernel<<<blocks, TC_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed,
                                                   (int)rpu, *out);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;

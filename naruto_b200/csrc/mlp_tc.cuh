@@ -1,9 +1,11 @@
 // Shared pieces of the tensor-core MLP kernels (forward_tc.cu, backward_tc.cu): weight staging, the TMEM column map,
 // the three-pass tf32 layer issue and the per-CTA prologue / epilogue.
 //
-// One CTA = 128 threads = one tile of 128 points; thread t owns point t = tensor-memory lane t.  Activations are
-// staged by their owner thread into TMEM as tf32 hi/lo pieces (A operand of tcgen05.mma, A-from-TMEM form); weights are
-// the B operand in shared memory (chunk-major K-major, hi and lo copies).
+// One CTA = 256 threads = one tile of 128 points; point r = tensor-memory lane r is shared by the thread pair
+// (r, r + 128) -- warps w and w + 4 may both touch lanes [32 (w%4), +32) -- and each thread of the pair handles one half of
+// the columns of every activation (kTcHalf() = threadIdx.x >> 7).  Activations are staged by their owner threads into
+// TMEM as tf32 hi/lo pieces (A operand of tcgen05.mma, A-from-TMEM form); weights are the B operand in shared memory
+// (chunk-major K-major, hi and lo copies).
 #pragma once
 #include "common.cuh"
 #include "umma.cuh"
@@ -13,13 +15,13 @@ using namespace umma;
 // shared-memory forward weight block (floats): chunk-major K-major B operands; the lo pieces follow at +FW_FLOATS
 #define FW_W1 0                   // [20 K-chunks][32 rows j][4]   k: hash 0..31 | oneblob 32..79
 #define FW_W2 (FW_W1 + 80 * 32)   // [ 8][16 rows i][4]            k: h1 0..31
-#define FW_W3 (FW_W2 + 32 * 16)   // [16][32 rows j][4]            k: oneblob 0..47 | geo 48..62 | 0
+#define FW_W3 (FW_W2 + 32 * 16)   // [16][32 rows j][4]            k: oneblob 0..47 | 0 (sdf slot) | geo 49..63
 #define FW_W4 (FW_W3 + 64 * 32)   // [ 8][16 rows i][4]            rows 3..15 = 0
 #define FW_FLOATS (FW_W4 + 32 * 16)
 
 // TMEM columns common to both kernels
 #define TC_ACC 0                  // [0,32)    accumulator of the current layer
-#define TC_AHI 32                 // [32,128)  A_hi: X0[32] | OneBlob[48] | geo[16]
+#define TC_AHI 32                 // [32,128)  A_hi: X0[32] | OneBlob[48] | o[16] = sdf (zero weight) + geo[15]
 #define TC_ALO 128                // [128,224) A_lo: same structure, the low-order pieces
 #define TA_X0 0
 #define TA_OB 32
@@ -45,7 +47,8 @@ __device__ __forceinline__ void load_weights_tc(float* sw, const NrtParams& prm)
   }
   for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
     const int j = i >> 6, k = i & 63;
-    put_split(sw, FW_W3 + ((k >> 2) * 32 + j) * 4 + (k & 3), k < 63 ? __ldg(prm.w3 + j * 63 + k) : 0.f);
+    // the colour net reads [oneblob | geo]; its A columns are [oneblob | o] with o[0] = sdf, so column 48 gets weight 0
+    put_split(sw, FW_W3 + ((k >> 2) * 32 + j) * 4 + (k & 3), k < 48 ? __ldg(prm.w3 + j * 63 + k) : k == 48 ? 0.f : __ldg(prm.w3 + j * 63 + k - 1));
   }
   for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
     const int r = i >> 5, k = i & 31;
@@ -123,6 +126,10 @@ __device__ __forceinline__ void stage8(const TileCtx& c, int col, const float* v
   tmem_st8(c.lane_tb + TC_ALO + col, lo);
 }
 
+#define TC_THREADS 256
+__device__ __forceinline__ int tc_half() { return (int)(threadIdx.x >> 7); }      // which half of the columns this thread owns
+__device__ __forceinline__ int tc_row() { return (int)(threadIdx.x & 127); }      // point / TMEM lane of this thread
+
 // common prologue: forward weights -> smem, barrier init, TMEM allocation.
 // smem_raw: [bar 8 | slot 4 | pad to 128 | weights hi | weights lo | kernel-specific ...]
 template <int NCOLS>
@@ -155,7 +162,7 @@ __device__ __forceinline__ void cta_prologue_finish(uint8_t* smem_raw, TileCtx& 
   __syncthreads();
   tc_fence_after();
   c.tb = *reinterpret_cast<uint32_t*>(smem_raw + 8);
-  c.lane_tb = c.tb + ((uint32_t)(32 * (threadIdx.x >> 5)) << 16);
+  c.lane_tb = c.tb + ((uint32_t)(32 * ((threadIdx.x >> 5) & 3)) << 16);
 }
 
 template <int NCOLS>
