@@ -228,14 +228,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_bwd_tc_kernel(const __gr
     // ---- dfeat = da1 W1[:, :32]  and the weight-gradient GEMM D += Y^T X over this tile's 128 points ----
     fence_async_smem();            // X^T / Y^T were written with generic st.shared; the MMA reads them through the async proxy
     layer_publish();
-    if (t == 0) {
+    if ((t >> 5) == 0) {
       tc_fence_after();
+      if (elect_one()) {
       issue_layer<32, 32>(c, TA_X0, bw_hi + BW_W1T * 4, bw_lo + BW_W1T * 4);
       constexpr uint32_t idesc = idesc_tf32(128, 160, 0, 0);
 #pragma unroll 4
       for (int ks = 0; ks < 16; ++ks)
         mma_tf32_ss(c.tb + TC_DW, desc_kmajor(yt_s, YT_ROWS, 2 * ks), desc_kmajor(xt_s, XT_ROWS, 2 * ks), idesc, !(first_tile && ks == 0));
       mma_commit(c.bar);
+      }
     }
     first_tile = false;
     layer_wait(c);

@@ -96,10 +96,12 @@ __device__ __forceinline__ void layer_wait(TileCtx& c) {
 template <int K, int N>
 __device__ __forceinline__ void run_layer(TileCtx& c, int a_col, uint32_t wh, uint32_t wl) {
   layer_publish();
-  if (threadIdx.x == 0) {
+  if ((threadIdx.x >> 5) == 0) {            // warp 0 stays converged; one elected lane issues
     tc_fence_after();
-    issue_layer<K, N>(c, a_col, wh, wl);
-    mma_commit(c.bar);
+    if (elect_one()) {
+      issue_layer<K, N>(c, a_col, wh, wl);
+      mma_commit(c.bar);
+    }
   }
   layer_wait(c);
 }
