@@ -37,8 +37,9 @@ UNIT = 'rays/s'
 N_SAMPLES_D = 117            # + n_range_d 11 = 128 samples per ray
 S = 128
 BYTES_PER_RAY_FWD = S * 1056 + 60          # hash gather 1024 B + uncert 32 B per point, + ray I/O
-BYTES_PER_POINT_BWD_MLP = 128 + 20 + 128   # decode_bwd: saved features in, dL/draw in, dL/dfeatures out
-BYTES_PER_POINT_SCATTER = 1024 + 128 + 4   # encode_bwd: one RMW per gathered entry + dL/dfeatures + z
+# backward (composite_bwd + fused MLP-backward/scatter): one RMW per gathered table entry and uncertainty corner
+# (1024 + 32 B), saved features in (128 B), raw + dL/draw (40 B), z (4 B); feature gradients never leave the SM
+BYTES_PER_POINT_BWD = 1024 + 32 + 128 + 40 + 4
 
 
 def peaks():
@@ -142,9 +143,7 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 def time_kernels(plan, ms, torch, flush, reps=10):
-    """CUDA-event time of each big kernel of the step, launched alone on the current stream, L2 flushed before."""
-    from naruto_b200 import _lib as L
-    import ctypes as C
+    """CUDA-event time of the two big launches of the step, each alone on the current stream, L2 flushed before."""
     B, Sn = ms.B, plan.S
     n_pts = B * Sn
     res = {}
@@ -161,35 +160,16 @@ def time_kernels(plan, ms, torch, flush, reps=10):
             ts.append(a.elapsed_time(b))
         return statistics.median(ts)
 
-    res['render_fwd_kernel'] = (timed(lambda: plan.render_fwd(ms.P, ms.rays_o, ms.rays_d, ms.target_d, ms.out, u=ms.u)),
-                                B * BYTES_PER_RAY_FWD)
+    res['render_fwd_tc_kernel'] = (timed(lambda: plan.render_fwd(ms.P, ms.rays_o, ms.rays_d, ms.target_d, ms.out, u=ms.u)),
+                                   B * BYTES_PER_RAY_FWD)
     plan.loss_partial(ms.out, ms.target_rgb, ms.target_d, ms.stats)
     plan.loss_finalize(ms.stats, ms.losses)
     gsave = ms.grad.clone()
     t_bwd = timed(lambda: plan.render_bwd(ms.P, ms.rays_o, ms.rays_d, ms.target_rgb, ms.target_d, ms.out, ms.stats, ms.loss_grad,
                                           ms.G, workspace=ms.ws_bwd))
-    # split the three backward kernels with the dedicated entry points is not possible through the public ABI
-    # without re-running; time the scatter alone and attribute the rest to composite+MLP backward
-    dfeat = ms.ws_bwd[n_pts * 5:n_pts * 37].view(n_pts, 32)
-    xs = _points(ms, torch)
-    t_scatter = timed(lambda: plan.encode_bwd(ms.P.grid, xs, dfeat, ms.G.grid))
-    res['encode_bwd_kernel'] = (t_scatter, n_pts * BYTES_PER_POINT_SCATTER)
-    res['composite_bwd+decode_bwd_kernel'] = (max(t_bwd - t_scatter, 1e-6), n_pts * BYTES_PER_POINT_BWD_MLP)
+    res['composite_bwd+decode_bwd_tc_kernel'] = (t_bwd, n_pts * BYTES_PER_POINT_BWD)
     ms.grad.copy_(gsave)
     return res
-
-
-_PTS = {}
-
-
-def _points(ms, torch):
-    """normalised sample points of the current batch (only for timing the scatter kernel through the public ABI)."""
-    key = id(ms)
-    if key not in _PTS:
-        b = torch.tensor(ms.plan.bound, device=ms.dev)
-        pts = ms.rays_o[:, None, :] + ms.rays_d[:, None, :] * ms.out.z_vals[:, :, None]
-        _PTS[key] = ((pts.reshape(-1, 3) - b[:, 0]) / (b[:, 1] - b[:, 0])).contiguous()
-    return _PTS[key]
 
 
 def run_ours(args):
@@ -297,8 +277,8 @@ def run_ours(args):
                 'traffic': None, 'peak_source': how,
                 'note': 'algorithmic bytes (SURVEY 8d) / CUDA-event time of the kernel launched alone, L2 flushed; at hash_size 16 '
                         'the 6.5 MB table is L2-resident so the gather fraction is an accounting convention',
-                'hash_gather': {'kernel': 'render_fwd_kernel', 'achieved': kern['render_fwd_kernel']['algorithmic_GB_per_s'],
-                                'frac': round(kern['render_fwd_kernel']['algorithmic_GB_per_s'] / hbm, 4)}}
+                'hash_gather': {'kernel': 'render_fwd_tc_kernel', 'achieved': kern['render_fwd_tc_kernel']['algorithmic_GB_per_s'],
+                                'frac': round(kern['render_fwd_tc_kernel']['algorithmic_GB_per_s'] / hbm, 4)}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu, k_cpu = 1024, 5
         tot, threads = cpu_reference(n_cpu, k_cpu, 1)

@@ -81,7 +81,7 @@ int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
     d.lv[l].hashed = ((uint64_t)res * res * res > size) ? 1u : 0u;
     d.lv[l].res2 = res * res;
     d.lv[l].magic = (uint32_t)((1ull << 32) / size);
-    d.lv[l].pad = 0;
+    d.lv[l].agg = res <= 64u ? 1u : 0u;
     offset += size;
   }
   NRT_REQUIRE(offset < (1ull << 31), "hash table too large for 32-bit entry offsets");
@@ -213,17 +213,15 @@ int nrt_decode_bwd(const NrtPlan* plan, const NrtParams* params, const float* x,
   NRT_REQUIRE(plan && x && draw && grads && workspace && n > 0, "decode_bwd arguments");
   if (int rc = check_params(params)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  float* feat = reinterpret_cast<float*>(workspace);          // [n,32] recomputed features, then overwritten by dfeat
+  float* feat = reinterpret_cast<float*>(workspace);          // [n,32] recomputed hash features
   if (int rc = launch_encode_fwd(plan, params->grid, x, n, feat, st)) return rc;
   PointSource src{x, nullptr, nullptr, nullptr, 1};
-  if (int rc = launch_decode_bwd(plan, params, src, n, feat, draw, feat, grads, st)) return rc;
-  if (grads->grid) return launch_encode_bwd(plan, params->grid, src, n, feat, 1.0f, grads->grid, nullptr, st);
-  return NRT_OK;
+  return launch_decode_bwd(plan, params, src, n, feat, draw, nullptr, grads, st);   // scatters into grads->grid itself
 }
 
 int64_t nrt_render_bwd_workspace(const NrtPlan* plan, int64_t n_rays) {
   if (!plan || n_rays < 0) return 0;
-  return n_rays * plan->dev.S * (5 + NRT_ENC) * (int64_t)sizeof(float);
+  return n_rays * plan->dev.S * 5 * (int64_t)sizeof(float);      // dL/d raw; feature gradients stay on chip
 }
 
 int nrt_render_bwd(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
@@ -236,12 +234,9 @@ int nrt_render_bwd(const NrtPlan* plan, const NrtParams* params, const float* ra
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_pts = n_rays * plan->dev.S;
   float* draw = reinterpret_cast<float*>(workspace);
-  float* dfeat = draw + n_pts * 5;
   if (int rc = launch_composite_bwd(plan, rend, target_rgb, target_d, n_rays, stats, loss_grad, draw, st)) return rc;
   PointSource src{nullptr, rays_o, rays_d, rend->z_vals, plan->dev.S};
-  if (int rc = launch_decode_bwd(plan, params, src, n_pts, rend->feat, draw, dfeat, grads, st)) return rc;
-  if (grads->grid) return launch_encode_bwd(plan, params->grid, src, n_pts, dfeat, 1.0f, grads->grid, nullptr, st);
-  return NRT_OK;
+  return launch_decode_bwd(plan, params, src, n_pts, rend->feat, draw, nullptr, grads, st);
 }
 
 int64_t nrt_smooth_workspace(const NrtPlan* plan, int32_t n) {

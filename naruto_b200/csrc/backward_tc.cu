@@ -11,7 +11,12 @@
 //               gradients as sub-blocks of a TMEM-resident accumulator that lives across all tiles of the CTA:
 //                   dW1 = D[0:32, 0:80]   dW3 = D[32:64, 32:80 | 81:96]   dW2 = D[64:80, 96:128]   dW4 = D[80:83, 128:160]
 //               (the other blocks are by-products the tensor pipe computes for free); flushed once per CTA with atomics.
-// TMEM: [0,32) accumulator | [32,128) A_hi | [128,224) A_lo | [224,384) D.   Shared memory ~186 KB.
+//   table grads: the CTA carries eight more warps (threads 256..511) that take each finished tile of dL/d hash-features from
+//               a two-stage shared-memory ring and scatter it into the table gradient with red.global.add.v2.f32 while the
+//               MLP warps work on the next tile, so the RED-bound scatter overlaps the latency-bound MLP chain and the
+//               feature gradients never travel through HBM.  Scatter thread = (point, 8 levels); on coarse levels runs of
+//               consecutive samples that fall into the same cell are merged with warp shuffles before the reduction.
+// TMEM: [0,32) accumulator | [32,128) A_hi | [128,224) A_lo | [224,384) D.   Shared memory ~221 KB.
 #include "mlp_tc.cuh"
 
 #define BT_COLS 512
@@ -35,6 +40,12 @@
 #define YR_DA3 32
 #define YR_DO 64
 #define YR_DC 80
+#define BWD_THREADS 512            // 256 MLP threads + 256 scatter threads
+#define RING_STAGES 2
+#define RING_DF_FLOATS (8 * 128 * 4)          // dfeat of one tile, chunk-major [8 chunks][128 rows][4]
+#define RING_STAGE_FLOATS (RING_DF_FLOATS + 4 * 128)   // + x0[128] x1[128] x2[128] active[128]
+#define BAR_FULL0 2                // named barriers: ring stage filled (2, 3) / drained (4, 5)
+#define BAR_EMPTY0 4
 #define XT_FLOATS (32 * XT_ROWS * 4)
 #define YT_FLOATS (32 * YT_ROWS * 4 + 160)     // the MMA reads 128 rows per chunk: slack behind the last chunk
 
@@ -44,7 +55,76 @@ __device__ __forceinline__ void put_split_bw(float* blk, int o, float v) {
   blk[o + BW_FLOATS] = v - h;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) decode_bwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
+// ---------------------------------------------------------------------------------------------
+// scatter warps (threads 256..511): thread = (row, half) takes levels 8*half .. 8*half+7 of its point.
+// On levels flagged `agg` consecutive rows (= consecutive samples of a ray) mostly share the trilinear cell: each lane
+// folds the contributions of the following lanes of its 8-lane window that sit in the same cell (3 shuffle steps) and only
+// the first lane of each run issues the reductions.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* __restrict__ s_lv, const float* __restrict__ ring,
+                                              float2* __restrict__ dgrid, int64_t n_tiles) {
+  const int sp = threadIdx.x - TC_THREADS, row = sp & 127, sh = sp >> 7, lane = threadIdx.x & 31;
+  const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  for (int k = 0; k < my_tiles; ++k) {
+    const int st = k & 1;
+    const float* stage = ring + st * RING_STAGE_FLOATS;
+    bar_sync(BAR_FULL0 + st, BWD_THREADS);
+    const float* xs = stage + RING_DF_FLOATS;
+    const float x0 = xs[row], x1 = xs[128 + row], x2 = xs[256 + row];
+    const bool active = xs[384 + row] != 0.f;
+#pragma unroll 1
+    for (int l = 0; l < (dgrid ? 8 : 0); ++l) {
+      const int lg = 8 * sh + l;
+      const DevLevel& L = s_lv[lg];
+      const float2 g = *reinterpret_cast<const float2*>(stage + ((lg >> 1) * 128 + row) * 4 + (lg & 1) * 2);
+      const bool nz = active && (g.x != 0.f || g.y != 0.f);
+      if (!L.agg) {
+        if (nz) {
+          uint32_t idx[8];
+          float w[8];
+          level_corners(L, x0, x1, x2, idx, w);
+          float2* base = dgrid + L.offset;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) red_add_f2(base + idx[c], w[c] * g.x, w[c] * g.y);
+        }
+      } else {
+        // every lane takes part in the shuffles; lanes without a gradient contribute zeros
+        uint32_t idx[8];
+        float w[8];
+        const LevelPos p = level_corners(L, x0, x1, x2, idx, w);
+        // same[s]: the lane 2^s places further in this 8-lane window sits in the same cell
+        bool same[3];
+#pragma unroll
+        for (int sdx = 0; sdx < 3; ++sdx) {
+          const int d = 1 << sdx;
+          const uint32_t o0 = __shfl_down_sync(0xffffffffu, p.g[0], d), o1 = __shfl_down_sync(0xffffffffu, p.g[1], d),
+                         o2 = __shfl_down_sync(0xffffffffu, p.g[2], d);
+          same[sdx] = ((lane & 7) + d < 8) && o0 == p.g[0] && o1 == p.g[1] && o2 == p.g[2];
+        }
+        const uint32_t q0 = __shfl_up_sync(0xffffffffu, p.g[0], 1), q1 = __shfl_up_sync(0xffffffffu, p.g[1], 1),
+                       q2 = __shfl_up_sync(0xffffffffu, p.g[2], 1);
+        const bool head = (lane & 7) == 0 || !(q0 == p.g[0] && q1 == p.g[1] && q2 == p.g[2]);
+        float2* base = dgrid + L.offset;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float v0 = nz ? w[c] * g.x : 0.f, v1 = nz ? w[c] * g.y : 0.f;
+#pragma unroll
+          for (int sdx = 0; sdx < 3; ++sdx) {
+            const float a0 = __shfl_down_sync(0xffffffffu, v0, 1 << sdx), a1 = __shfl_down_sync(0xffffffffu, v1, 1 << sdx);
+            if (same[sdx]) {
+              v0 += a0;
+              v1 += a1;
+            }
+          }
+          if (head && (v0 != 0.f || v1 != 0.f)) red_add_f2(base + idx[c], v0, v1);
+        }
+      }
+    }
+    if (k + RING_STAGES < my_tiles) bar_arrive(BAR_EMPTY0 + st, BWD_THREADS);
+  }
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
                                                                       const PointSource src, int64_t n_pts,
                                                                       const float* __restrict__ feat,
                                                                       const float* __restrict__ draw, float* __restrict__ dfeat,
@@ -56,21 +136,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_bwd_tc_kernel(const __gr
   float* w4s = bw + 2 * BW_FLOATS;        // w4 as stored [3][32] (+ pad)
   float* xt = w4s + 128;
   float* yt = xt + XT_FLOATS;
-  const int t = threadIdx.x, half = tc_half(), row = tc_row();
-  for (int i = t; i < 16 * 32; i += TC_THREADS) {  // W3G[n][j] = w3[j][48 + n - 1] (n >= 1): output column n is d o[n]
+  float* ring = yt + YT_FLOATS;
+  __shared__ DevLevel s_lv[NRT_L];
+  const int t = threadIdx.x, half = tc_half() & 1, row = tc_row();
+  if (t < NRT_L) s_lv[t] = P.lv[t];
+  for (int i = t; i < 16 * 32; i += BWD_THREADS) {  // W3G[n][j] = w3[j][48 + n - 1] (n >= 1): output column n is d o[n]
     const int n = i >> 5, j = i & 31;
     put_split_bw(bw, BW_W3G + ((j >> 2) * 16 + n) * 4 + (j & 3), n >= 1 ? __ldg(prm.w3 + j * 63 + NRT_OB + n - 1) : 0.f);
   }
-  for (int i = t; i < 32 * 16; i += TC_THREADS) {  // W2T[j][i] = w2[i][j]
+  for (int i = t; i < 32 * 16; i += BWD_THREADS) {  // W2T[j][i] = w2[i][j]
     const int j = i >> 4, ii = i & 15;
     put_split_bw(bw, BW_W2T + ((ii >> 2) * 32 + j) * 4 + (ii & 3), __ldg(prm.w2 + ii * 32 + j));
   }
-  for (int i = t; i < 32 * 32; i += TC_THREADS) {  // W1T[f][j] = w1[j][f]
+  for (int i = t; i < 32 * 32; i += BWD_THREADS) {  // W1T[f][j] = w1[j][f]
     const int f = i >> 5, j = i & 31;
     put_split_bw(bw, BW_W1T + ((j >> 2) * 32 + f) * 4 + (j & 3), __ldg(prm.w1 + j * 80 + f));
   }
-  for (int i = t; i < 128; i += TC_THREADS) w4s[i] = i < 96 ? __ldg(prm.w4 + i) : 0.f;
-  for (int i = t; i < YT_FLOATS; i += TC_THREADS) yt[i] = 0.f;   // rows 83.. and the slack stay zero for the whole kernel
+  for (int i = t; i < 128; i += BWD_THREADS) w4s[i] = i < 96 ? __ldg(prm.w4 + i) : 0.f;
+  for (int i = t; i < YT_FLOATS; i += BWD_THREADS) yt[i] = 0.f;   // rows 83.. and the slack stay zero for the whole kernel
   cta_prologue_finish(smem_raw, c);
   const uint32_t bw_hi = smem_u32(bw), bw_lo = smem_u32(bw + BW_FLOATS);
   const uint32_t xt_s = smem_u32(xt), yt_s = smem_u32(yt);
@@ -80,7 +163,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_bwd_tc_kernel(const __gr
 
   const int64_t n_tiles = (n_pts + 127) / 128;
   bool first_tile = true;
-  for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+  if (t >= TC_THREADS) {
+    scatter_warps(P, s_lv, ring, reinterpret_cast<float2*>(grads.grid), n_tiles);
+  } else {
+  int k = 0;                      // tiles done by this CTA: ring stage = k & 1
+  for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++k) {
     const int64_t pt = tl * 128 + row;
     const bool active = pt < n_pts;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
@@ -250,6 +337,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_bwd_tc_kernel(const __gr
         for (int q = 0; q < 4; ++q)
           reinterpret_cast<float4*>(dfeat + pt * NRT_ENC + 16 * half)[q] = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
       }
+      // hand the tile to the scatter warps through the ring
+      const int st = k & 1;
+      float* stage = ring + st * RING_STAGE_FLOATS;
+      if (k >= RING_STAGES) bar_sync(BAR_EMPTY0 + st, BWD_THREADS);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sts4(stage + ((4 * half + q) * 128 + row) * 4, df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
+      if (half == 0) {
+        float* xs = stage + RING_DF_FLOATS;
+        xs[row] = x0;
+        xs[128 + row] = x1;
+        xs[256 + row] = x2;
+        xs[384 + row] = active ? 1.0f : 0.0f;
+      }
+      bar_arrive(BAR_FULL0 + st, BWD_THREADS);
     }
     // uncertainty grid: raw[...,4] is the trilinear sample itself
     if (half == 1 && active && grads.uncert && du != 0.f) {
@@ -262,11 +363,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_bwd_tc_kernel(const __gr
       }
     }
   }
+  }  // MLP threads
   // ---- flush the weight gradients: the thread pair of row r holds row r of D, half 0 columns 0..79, half 1 80..159 ----
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (!first_tile) {
+  if (t < TC_THREADS && !first_tile) {
     for (int cb = 80 * half; cb < 80 * half + 80; cb += 16) {
       float v[16];
       tmem_ld16(c.lane_tb + TC_DW + cb, v);
@@ -293,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) decode_bwd_tc_kernel(const __gr
 }
 
 size_t decode_bwd_tc_smem() {
-  return TC_SMEM_WEIGHTS + (size_t)(2 * BW_FLOATS + 128 + XT_FLOATS + YT_FLOATS) * sizeof(float);
+  return TC_SMEM_WEIGHTS + (size_t)(2 * BW_FLOATS + 128 + XT_FLOATS + YT_FLOATS + RING_STAGES * RING_STAGE_FLOATS) * sizeof(float);
 }
 
 int launch_decode_bwd(const NrtPlan* plan, const NrtParams* prm, const PointSource& src, int64_t n_pts, const float* feat,
@@ -307,7 +409,7 @@ int launch_decode_bwd(const NrtPlan* plan, const NrtParams* prm, const PointSour
   }
   const int64_t tiles = (n_pts + 127) / 128;
   const int blocks = (int)(tiles < plan->sm_count ? tiles : plan->sm_count);
-  decode_bwd_tc_kernel<<<blocks, TC_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, draw, dfeat, *grads);
+  decode_bwd_tc_kernel<<<blocks, BWD_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, draw, dfeat, *grads);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

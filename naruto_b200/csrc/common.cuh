@@ -28,7 +28,7 @@ struct DevLevel {
   uint32_t hashed;    // 1: coherent prime hash, 0: dense stride walk
   uint32_t res2;      // res*res (mod 2^32)
   uint32_t magic;     // floor(2^32 / size): umulhi(v, magic) is floor(v/size) or one less, for any 32-bit v
-  uint32_t pad;
+  uint32_t agg;       // 1: cells are coarse relative to the sample spacing -> merge runs of samples before the gradient RED
 };
 
 struct DevPlan {
@@ -142,8 +142,8 @@ __device__ __forceinline__ float corner_weight(const LevelPos& p, int c) {
 }
 
 // all eight corner entries and weights of one level; one (warp-uniform) branch per level, none per corner
-__device__ __forceinline__ void level_corners(const DevLevel& L, float x0, float x1, float x2, uint32_t* __restrict__ idx,
-                                              float* __restrict__ w) {
+__device__ __forceinline__ LevelPos level_corners(const DevLevel& L, float x0, float x1, float x2, uint32_t* __restrict__ idx,
+                                                  float* __restrict__ w) {
   const LevelPos p = level_pos(L, x0, x1, x2);
   const float wx[2] = {1.0f - p.f[0], p.f[0]}, wy[2] = {1.0f - p.f[1], p.f[1]}, wz[2] = {1.0f - p.f[2], p.f[2]};
   float wxy[4];
@@ -165,6 +165,7 @@ __device__ __forceinline__ void level_corners(const DevLevel& L, float x0, float
 #pragma unroll
     for (int c = 0; c < 8; ++c) idx[c] = mod_size(L, base + (c & 1) + ((c >> 1) & 1) * L.res + (c >> 2) * L.res2);
   }
+  return p;
 }
 
 // gathers one level: returns the two interpolated features

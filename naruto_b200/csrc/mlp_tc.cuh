@@ -27,6 +27,7 @@ using namespace umma;
 #define TA_OB 32
 #define TA_GEO 80
 
+#define TC_THREADS 256            // MLP threads per CTA (thread pairs of 128 rows)
 #define TC_SMEM_HEADER 128
 #define TC_SMEM_WEIGHTS (TC_SMEM_HEADER + 2 * FW_FLOATS * 4)
 
@@ -78,11 +79,15 @@ __device__ __forceinline__ void issue_layer(const TileCtx& c, int a_col, uint32_
   for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wl, N, 2 * ks), idesc, true);
 }
 
-// all threads: make this thread's TMEM stores visible, then meet at the CTA barrier
+// The 256 MLP threads (threads 0..255 of the CTA) meet on named barrier 1, so a CTA may carry extra warps with other roles.
+#define TC_BAR_MLP 1
+__device__ __forceinline__ void tc_sync() { bar_sync(TC_BAR_MLP, TC_THREADS); }
+
+// MLP threads: make this thread's TMEM stores visible, then meet at the group barrier
 __device__ __forceinline__ void layer_publish() {
   tmem_st_wait();
   tc_fence_before();
-  __syncthreads();
+  tc_sync();
 }
 // all threads: wait until the MMAs committed to c.bar have completed
 __device__ __forceinline__ void layer_wait(TileCtx& c) {
@@ -128,7 +133,6 @@ __device__ __forceinline__ void stage8(const TileCtx& c, int col, const float* v
   tmem_st8(c.lane_tb + TC_ALO + col, lo);
 }
 
-#define TC_THREADS 256
 __device__ __forceinline__ int tc_half() { return (int)(threadIdx.x >> 7); }      // which half of the columns this thread owns
 __device__ __forceinline__ int tc_row() { return (int)(threadIdx.x & 127); }      // point / TMEM lane of this thread
 

@@ -35,6 +35,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// named CTA barriers (ids 1..15; id 0 is __syncthreads): sync = arrive and wait, arrive = arrive only.  A barrier
+// completes when `n` threads (a multiple of 32) have arrived; st.shared before the arrive are visible after the sync.
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
