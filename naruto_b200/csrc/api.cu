@@ -81,7 +81,7 @@ int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
     d.lv[l].hashed = ((uint64_t)res * res * res > size) ? 1u : 0u;
     d.lv[l].res2 = res * res;
     d.lv[l].magic = (uint32_t)((1ull << 32) / size);
-    d.lv[l].agg = res <= 64u ? 1u : 0u;
+    d.lv[l].agg = res <= 32u ? 3u : res <= 64u ? 2u : 0u;
     offset += size;
   }
   NRT_REQUIRE(offset < (1ull << 31), "hash table too large for 32-bit entry offsets");

@@ -56,10 +56,11 @@ __device__ __forceinline__ void put_split_bw(float* blk, int o, float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// scatter warps (threads 256..511): thread = (row, half) takes levels 8*half .. 8*half+7 of its point.
+// scatter warps (threads 256..511): thread = (row, half) takes eight levels of its point (4 coarse + 4 fine per half).
 // On levels flagged `agg` consecutive rows (= consecutive samples of a ray) mostly share the trilinear cell: each lane
-// folds the contributions of the following lanes of its 8-lane window that sit in the same cell (3 shuffle steps) and only
-// the first lane of each run issues the reductions.
+// folds the contributions of the following lanes of its window (8 lanes / 3 shuffle steps on the coarsest levels, 4 lanes /
+// 2 steps on the medium ones; DevLevel::agg) that sit in the same cell, and only the first lane of each run issues the
+// reductions.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* __restrict__ s_lv, const float* __restrict__ ring,
                                               float2* __restrict__ dgrid, int64_t n_tiles) {
@@ -74,7 +75,7 @@ __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* 
     const bool active = xs[384 + row] != 0.f;
 #pragma unroll 1
     for (int l = 0; l < (dgrid ? 8 : 0); ++l) {
-      const int lg = 8 * sh + l;
+      const int lg = 4 * (2 * (l >> 2) + sh) + (l & 3);      // half 0: levels 0-3, 8-11; half 1: 4-7, 12-15 (balances the halves)
       const DevLevel& L = s_lv[lg];
       const float2 g = *reinterpret_cast<const float2*>(stage + ((lg >> 1) * 128 + row) * 4 + (lg & 1) * 2);
       const bool nz = active && (g.x != 0.f || g.y != 0.f);
@@ -92,28 +93,31 @@ __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* 
         uint32_t idx[8];
         float w[8];
         const LevelPos p = level_corners(L, x0, x1, x2, idx, w);
-        // same[s]: the lane 2^s places further in this 8-lane window sits in the same cell
+        // same[s]: the lane 2^s places further in this window of 2^agg lanes sits in the same cell
+        const int wmask = (1 << L.agg) - 1;
         bool same[3];
 #pragma unroll
         for (int sdx = 0; sdx < 3; ++sdx) {
           const int d = 1 << sdx;
           const uint32_t o0 = __shfl_down_sync(0xffffffffu, p.g[0], d), o1 = __shfl_down_sync(0xffffffffu, p.g[1], d),
                          o2 = __shfl_down_sync(0xffffffffu, p.g[2], d);
-          same[sdx] = ((lane & 7) + d < 8) && o0 == p.g[0] && o1 == p.g[1] && o2 == p.g[2];
+          same[sdx] = ((lane & wmask) + d <= wmask) && o0 == p.g[0] && o1 == p.g[1] && o2 == p.g[2];
         }
         const uint32_t q0 = __shfl_up_sync(0xffffffffu, p.g[0], 1), q1 = __shfl_up_sync(0xffffffffu, p.g[1], 1),
                        q2 = __shfl_up_sync(0xffffffffu, p.g[2], 1);
-        const bool head = (lane & 7) == 0 || !(q0 == p.g[0] && q1 == p.g[1] && q2 == p.g[2]);
+        const bool head = (lane & wmask) == 0 || !(q0 == p.g[0] && q1 == p.g[1] && q2 == p.g[2]);
         float2* base = dgrid + L.offset;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float v0 = nz ? w[c] * g.x : 0.f, v1 = nz ? w[c] * g.y : 0.f;
 #pragma unroll
           for (int sdx = 0; sdx < 3; ++sdx) {
-            const float a0 = __shfl_down_sync(0xffffffffu, v0, 1 << sdx), a1 = __shfl_down_sync(0xffffffffu, v1, 1 << sdx);
-            if (same[sdx]) {
-              v0 += a0;
-              v1 += a1;
+            if (sdx < (int)L.agg) {          // warp-uniform: 2 steps on the medium levels, 3 on the coarsest
+              const float a0 = __shfl_down_sync(0xffffffffu, v0, 1 << sdx), a1 = __shfl_down_sync(0xffffffffu, v1, 1 << sdx);
+              if (same[sdx]) {
+                v0 += a0;
+                v1 += a1;
+              }
             }
           }
           if (head && (v0 != 0.f || v1 != 0.f)) red_add_f2(base + idx[c], v0, v1);

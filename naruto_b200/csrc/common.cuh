@@ -28,7 +28,7 @@ struct DevLevel {
   uint32_t hashed;    // 1: coherent prime hash, 0: dense stride walk
   uint32_t res2;      // res*res (mod 2^32)
   uint32_t magic;     // floor(2^32 / size): umulhi(v, magic) is floor(v/size) or one less, for any 32-bit v
-  uint32_t agg;       // 1: cells are coarse relative to the sample spacing -> merge runs of samples before the gradient RED
+  uint32_t agg;       // > 0: cells are coarse relative to the sample spacing: merge runs of up to 2^agg samples before the gradient RED
 };
 
 struct DevPlan {
