@@ -11,7 +11,7 @@
 //               gradients as sub-blocks of a TMEM-resident accumulator that lives across all tiles of the CTA:
 //                   dW1 = D[0:32, 0:80]   dW3 = D[32:64, 32:80 | 81:96]   dW2 = D[64:80, 96:128]   dW4 = D[80:83, 128:160]
 //               (the other blocks are by-products the tensor pipe computes for free); flushed once per CTA with atomics.
-//   table grads: the CTA carries eight more warps (threads 256..511) that take each finished tile of dL/d hash-features from
+//   table grads: the CTA carries eight more warps (threads 0..255; the MLP group is threads 256..511) that take each finished tile of dL/d hash-features from
 //               a two-stage shared-memory ring and scatter it into the table gradient with red.global.add.v2.f32 while the
 //               MLP warps work on the next tile, so the RED-bound scatter overlaps the latency-bound MLP chain and the
 //               feature gradients never travel through HBM.  Scatter thread = (point, 8 levels); on coarse levels runs of
@@ -56,7 +56,7 @@ __device__ __forceinline__ void put_split_bw(float* blk, int o, float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// scatter warps (threads 256..511): thread = (row, half) takes eight levels of its point (4 coarse + 4 fine per half).
+// scatter warps (threads 0..255): thread = (row, half) takes eight levels of its point (4 coarse + 4 fine per half).
 // On levels flagged `agg` consecutive rows (= consecutive samples of a ray) mostly share the trilinear cell: each lane
 // folds the contributions of the following lanes of its window (8 lanes / 3 shuffle steps on the coarsest levels, 4 lanes /
 // 2 steps on the medium ones; DevLevel::agg) that sit in the same cell, and only the first lane of each run issues the
@@ -64,7 +64,7 @@ __device__ __forceinline__ void put_split_bw(float* blk, int o, float v) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* __restrict__ s_lv, const float* __restrict__ ring,
                                               float2* __restrict__ dgrid, int64_t n_tiles) {
-  const int sp = threadIdx.x - TC_THREADS, row = sp & 127, sh = sp >> 7, lane = threadIdx.x & 31;
+  const int sp = threadIdx.x, row = sp & 127, sh = sp >> 7, lane = threadIdx.x & 31;
   const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   for (int k = 0; k < my_tiles; ++k) {
     const int st = k & 1;
@@ -88,8 +88,9 @@ __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* 
 #pragma unroll
           for (int c = 0; c < 8; ++c) red_add_f2(base + idx[c], w[c] * g.x, w[c] * g.y);
         }
-      } else {
-        // every lane takes part in the shuffles; lanes without a gradient contribute zeros
+      } else if (__any_sync(0xffffffffu, nz)) {
+        // every lane takes part in the shuffles; lanes without a gradient contribute zeros (a warp whose 32 samples all
+        // lie behind the surface has nothing to add and skips the level)
         uint32_t idx[8];
         float w[8];
         const LevelPos p = level_corners(L, x0, x1, x2, idx, w);
@@ -167,7 +168,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
 
   const int64_t n_tiles = (n_pts + 127) / 128;
   bool first_tile = true;
-  if (t >= TC_THREADS) {
+  // Warp roles: the SM's issue arbiter favours high warp ids, so the latency-critical MLP chain takes warps 8..15 and
+  // the throughput-bound scatter takes warps 0..7.
+  if (t < TC_THREADS) {
     scatter_warps(P, s_lv, ring, reinterpret_cast<float2*>(grads.grid), n_tiles);
   } else {
   int k = 0;                      // tiles done by this CTA: ring stage = k & 1
@@ -319,14 +322,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
     // ---- dfeat = da1 W1[:, :32]  and the weight-gradient GEMM D += Y^T X over this tile's 128 points ----
     fence_async_smem();            // X^T / Y^T were written with generic st.shared; the MMA reads them through the async proxy
     layer_publish();
-    if ((t >> 5) == 0) {
+    if (tc_issuer_warp()) {
       tc_fence_after();
       if (elect_one()) {
       issue_layer<32, 32>(c, TA_X0, bw_hi + BW_W1T * 4, bw_lo + BW_W1T * 4);
       constexpr uint32_t idesc = idesc_tf32(128, 160, 0, 0);
-#pragma unroll 4
+      const uint64_t yd = smem_desc(yt_s, YT_ROWS * 16, 128), xd = smem_desc(xt_s, XT_ROWS * 16, 128);
+#pragma unroll
       for (int ks = 0; ks < 16; ++ks)
-        mma_tf32_ss(c.tb + TC_DW, desc_kmajor(yt_s, YT_ROWS, 2 * ks), desc_kmajor(xt_s, XT_ROWS, 2 * ks), idesc, !(first_tile && ks == 0));
+        mma_tf32_ss(c.tb + TC_DW, yd + (uint64_t)(2 * YT_ROWS * ks), xd + (uint64_t)(2 * XT_ROWS * ks), idesc, !(first_tile && ks == 0));
       mma_commit(c.bar);
       }
     }
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (t < TC_THREADS && !first_tile) {
+  if (t >= TC_THREADS && !first_tile) {
     for (int cb = 80 * half; cb < 80 * half + 80; cb += 16) {
       float v[16];
       tmem_ld16(c.lane_tb + TC_DW + cb, v);

@@ -71,12 +71,15 @@ template <int K, int N>
 __device__ __forceinline__ void issue_layer(const TileCtx& c, int a_col, uint32_t wh, uint32_t wl) {
   constexpr uint32_t idesc = idesc_tf32(128, N, 0, 0);
   const uint32_t d = c.tb + TC_ACC;
+  const uint32_t ah = c.tb + TC_AHI + a_col, al = c.tb + TC_ALO + a_col;
+  // one descriptor per operand; a K step of 8 (two 16-byte chunks of N rows) advances the start-address field by 2*N
+  const uint64_t bh = smem_desc(wh, N * 16, 128), bl = smem_desc(wl, N * 16, 128);
 #pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wh, N, 2 * ks), idesc, ks > 0);
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, ah + 8 * ks, bh + (uint64_t)(2 * N * ks), idesc, ks > 0);
 #pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_ALO + a_col + 8 * ks, desc_kmajor(wh, N, 2 * ks), idesc, true);
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, al + 8 * ks, bh + (uint64_t)(2 * N * ks), idesc, true);
 #pragma unroll
-  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, c.tb + TC_AHI + a_col + 8 * ks, desc_kmajor(wl, N, 2 * ks), idesc, true);
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, ah + 8 * ks, bl + (uint64_t)(2 * N * ks), idesc, true);
 }
 
 // The 256 MLP threads (threads 0..255 of the CTA) meet on named barrier 1, so a CTA may carry extra warps with other roles.
@@ -97,11 +100,14 @@ __device__ __forceinline__ void layer_wait(TileCtx& c) {
   tc_fence_after();
 }
 
-// publish -> thread 0 issues one layer -> wait for its accumulator
+// first warp of the MLP group (the group is 8 consecutive warps starting at a multiple of 8)
+__device__ __forceinline__ bool tc_issuer_warp() { return ((threadIdx.x >> 5) & 7) == 0; }
+
+// publish -> one elected lane of the group's first warp issues one layer -> wait for its accumulator
 template <int K, int N>
 __device__ __forceinline__ void run_layer(TileCtx& c, int a_col, uint32_t wh, uint32_t wl) {
   layer_publish();
-  if ((threadIdx.x >> 5) == 0) {            // warp 0 stays converged; one elected lane issues
+  if (tc_issuer_warp()) {                   // the warp stays converged; one elected lane issues
     tc_fence_after();
     if (elect_one()) {
       issue_layer<K, N>(c, a_col, wh, wl);
