@@ -3,8 +3,9 @@
 //
 // One persistent CTA per SM, 256 threads, thread pair (r, r+128) = point r of the tile = TMEM lane r, each thread owning
 // half of the columns of every activation / gradient (mlp_tc.cuh).  Per tile of 128 points:
-//   recompute   h1 = relu(W1 [hash|oneblob]), o = W2 h1, h3 = relu(W3 [oneblob|geo])            (3 tcgen05 layers, 3xTF32)
-//   data grads  dh3 = W4^T dc (SIMT, 96 FMA) ; dgeo = W3g^T da3 ; dh1 = W2^T do ; dfeat = W1h^T da1   (3 tcgen05 layers, 3xTF32)
+//   recompute   h1 = relu(W1 [hash|oneblob]) ; [o | a3] = [W2 h1 | W23 h1 + W3_ob oneblob], h3 = relu(a3)   (2 tcgen05 phases)
+//   data grads  dh3 = W4^T dc (SIMT, 96 FMA) ; [dh1 | do] from [da3 | dsdf] ; dfeat = W1h^T da1               (2 tcgen05 phases)
+//               (layer fusion through W23 = W3_geo W2_geo, mlp_tc.cuh: four dependent phases per tile instead of six; 3xTF32)
 //   weight grads: every activation X = [hash|oneblob|geo|h1|h3] (160) and every upstream gradient Y = [da1|da3|do|dc] (88)
 //               is also scattered, transposed and rounded to tf32, into shared memory as K-major operands over the point
 //               index, and ONE tcgen05 GEMM  D[128 x 160] += Y^T X  (K = 128 points, 16 MMAs) accumulates all four weight
@@ -12,7 +13,7 @@
 //                   dW1 = D[0:32, 0:80]   dW3 = D[32:64, 32:80 | 81:96]   dW2 = D[64:80, 96:128]   dW4 = D[80:83, 128:160]
 //               (the other blocks are by-products the tensor pipe computes for free); flushed once per CTA with atomics.
 //   table grads: the CTA carries eight more warps (threads 0..255; the MLP group is threads 256..511) that take each finished tile of dL/d hash-features from
-//               a two-stage shared-memory ring and scatter it into the table gradient with red.global.add.v2.f32 while the
+//               a shared-memory hand-over slot and scatter it into the table gradient with red.global.add.v2.f32 while the
 //               MLP warps work on the next tile, so the RED-bound scatter overlaps the latency-bound MLP chain and the
 //               feature gradients never travel through HBM.  Scatter thread = (point, 8 levels); on coarse levels runs of
 //               consecutive samples that fall into the same cell are merged with warp shuffles before the reduction.
@@ -23,9 +24,10 @@
 #define TC_DW 224
 
 // backward weight block (floats), hi at +0 and lo at +BW_FLOATS
-#define BW_W3G 0                   // d o[n] = da3 W3[:,48+n-1]: [8 K-chunks j][16 rows n][4]   row 0 = 0 (the sdf slot)
-#define BW_W2T (BW_W3G + 32 * 16)  // dh1 = do W2:             [4 K-chunks i][32 rows j][4]
-#define BW_W1T (BW_W2T + 16 * 32)  // dfeat = da1 W1[:, :32]:  [8 K-chunks j][32 rows f][4]
+// phase B12 on A = [da3 (32) | dsdf, 0 x 7] (K = 40): columns 0..31 = dh1 = W23^T da3 + W2[0,:]^T dsdf,
+//                                                   columns 32..47 = d o = [dsdf, W3[:, 48:63]^T da3]
+#define BW_B12 0                   // [10 K-chunks][48 rows][4]
+#define BW_W1T (BW_B12 + 40 * 48)  // dfeat = da1 W1[:, :32]:  [8 K-chunks j][32 rows f][4]
 #define BW_FLOATS (BW_W1T + 32 * 32)
 
 // transposed operands of the weight-gradient GEMM: buf[32 chunks of 4 points][R rows][4 points], R = 1 (mod 8)
@@ -40,12 +42,11 @@
 #define YR_DA3 32
 #define YR_DO 64
 #define YR_DC 80
-#define BWD_THREADS 512            // 256 MLP threads + 256 scatter threads
-#define RING_STAGES 2
+#define BWD_THREADS 512            // 256 scatter threads (warps 0..7) + 256 MLP threads (warps 8..15)
 #define RING_DF_FLOATS (8 * 128 * 4)          // dfeat of one tile, chunk-major [8 chunks][128 rows][4]
 #define RING_STAGE_FLOATS (RING_DF_FLOATS + 4 * 128)   // + x0[128] x1[128] x2[128] active[128]
-#define BAR_FULL0 2                // named barriers: ring stage filled (2, 3) / drained (4, 5)
-#define BAR_EMPTY0 4
+#define BAR_FULL 2                 // named barriers: hand-over slot filled / drained
+#define BAR_EMPTY 3
 #define XT_FLOATS (32 * XT_ROWS * 4)
 #define YT_FLOATS (32 * YT_ROWS * 4 + 160)     // the MMA reads 128 rows per chunk: slack behind the last chunk
 
@@ -56,7 +57,8 @@ __device__ __forceinline__ void put_split_bw(float* blk, int o, float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// scatter warps (threads 0..255): thread = (row, half) takes eight levels of its point (4 coarse + 4 fine per half).
+// scatter warps (threads 0..255): warp w takes levels w and w + 8 (one coarse, one fine) of all 128 rows of the tile, 32
+// consecutive rows at a time, so every warp sees the same mix of samples in front of and behind the surface.
 // On levels flagged `agg` consecutive rows (= consecutive samples of a ray) mostly share the trilinear cell: each lane
 // folds the contributions of the following lanes of its window (8 lanes / 3 shuffle steps on the coarsest levels, 4 lanes /
 // 2 steps on the medium ones; DevLevel::agg) that sit in the same cell, and only the first lane of each run issues the
@@ -64,36 +66,34 @@ __device__ __forceinline__ void put_split_bw(float* blk, int o, float v) {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* __restrict__ s_lv, const float* __restrict__ ring,
                                               float2* __restrict__ dgrid, int64_t n_tiles) {
-  const int sp = threadIdx.x, row = sp & 127, sh = sp >> 7, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   for (int k = 0; k < my_tiles; ++k) {
-    const int st = k & 1;
-    const float* stage = ring + st * RING_STAGE_FLOATS;
-    bar_sync(BAR_FULL0 + st, BWD_THREADS);
+    const float* stage = ring;
+    bar_sync(BAR_FULL, BWD_THREADS);
     const float* xs = stage + RING_DF_FLOATS;
-    const float x0 = xs[row], x1 = xs[128 + row], x2 = xs[256 + row];
-    const bool active = xs[384 + row] != 0.f;
+    // iteration = (block of 32 consecutive rows, one of this warp's two levels)
 #pragma unroll 1
-    for (int l = 0; l < (dgrid ? 8 : 0); ++l) {
-      const int lg = 4 * (2 * (l >> 2) + sh) + (l & 3);      // half 0: levels 0-3, 8-11; half 1: 4-7, 12-15 (balances the halves)
+    for (int it = 0; it < (dgrid ? 8 : 0); ++it) {
+      const int row = 32 * (it >> 1) + lane;
+      const int lg = warp + 8 * (it & 1);
+      const float x0 = xs[row], x1 = xs[128 + row], x2 = xs[256 + row];
+      const bool active = xs[384 + row] != 0.f;
       const DevLevel& L = s_lv[lg];
       const float2 g = *reinterpret_cast<const float2*>(stage + ((lg >> 1) * 128 + row) * 4 + (lg & 1) * 2);
       const bool nz = active && (g.x != 0.f || g.y != 0.f);
+      if (!__any_sync(0xffffffffu, nz)) continue;          // e.g. 32 samples behind the surface: nothing to add
+      uint32_t idx[8];
+      float w[8];
+      const LevelPos p = level_corners(L, x0, x1, x2, idx, w);
+      float2* base = dgrid + L.offset;
       if (!L.agg) {
         if (nz) {
-          uint32_t idx[8];
-          float w[8];
-          level_corners(L, x0, x1, x2, idx, w);
-          float2* base = dgrid + L.offset;
 #pragma unroll
           for (int c = 0; c < 8; ++c) red_add_f2(base + idx[c], w[c] * g.x, w[c] * g.y);
         }
-      } else if (__any_sync(0xffffffffu, nz)) {
-        // every lane takes part in the shuffles; lanes without a gradient contribute zeros (a warp whose 32 samples all
-        // lie behind the surface has nothing to add and skips the level)
-        uint32_t idx[8];
-        float w[8];
-        const LevelPos p = level_corners(L, x0, x1, x2, idx, w);
+      } else {
+        // every lane takes part in the shuffles; lanes without a gradient contribute zeros.
         // same[s]: the lane 2^s places further in this window of 2^agg lanes sits in the same cell
         const int wmask = (1 << L.agg) - 1;
         bool same[3];
@@ -107,7 +107,6 @@ __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* 
         const uint32_t q0 = __shfl_up_sync(0xffffffffu, p.g[0], 1), q1 = __shfl_up_sync(0xffffffffu, p.g[1], 1),
                        q2 = __shfl_up_sync(0xffffffffu, p.g[2], 1);
         const bool head = (lane & wmask) == 0 || !(q0 == p.g[0] && q1 == p.g[1] && q2 == p.g[2]);
-        float2* base = dgrid + L.offset;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float v0 = nz ? w[c] * g.x : 0.f, v1 = nz ? w[c] * g.y : 0.f;
@@ -125,7 +124,7 @@ __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* 
         }
       }
     }
-    if (k + RING_STAGES < my_tiles) bar_arrive(BAR_EMPTY0 + st, BWD_THREADS);
+    if (k + 1 < my_tiles) bar_arrive(BAR_EMPTY, BWD_THREADS);
   }
 }
 
@@ -145,13 +144,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
   __shared__ DevLevel s_lv[NRT_L];
   const int t = threadIdx.x, half = tc_half() & 1, row = tc_row();
   if (t < NRT_L) s_lv[t] = P.lv[t];
-  for (int i = t; i < 16 * 32; i += BWD_THREADS) {  // W3G[n][j] = w3[j][48 + n - 1] (n >= 1): output column n is d o[n]
-    const int n = i >> 5, j = i & 31;
-    put_split_bw(bw, BW_W3G + ((j >> 2) * 16 + n) * 4 + (j & 3), n >= 1 ? __ldg(prm.w3 + j * 63 + NRT_OB + n - 1) : 0.f);
-  }
-  for (int i = t; i < 32 * 16; i += BWD_THREADS) {  // W2T[j][i] = w2[i][j]
-    const int j = i >> 4, ii = i & 15;
-    put_split_bw(bw, BW_W2T + ((ii >> 2) * 32 + j) * 4 + (ii & 3), __ldg(prm.w2 + ii * 32 + j));
+  for (int i = t; i < 48 * 40; i += BWD_THREADS) {  // phase B12 operand, see BW_B12
+    const int n = i / 40, k = i % 40;
+    float v = 0.f;
+    if (n < 32) v = k < 32 ? w23_at(prm, k, n) : k == 32 ? __ldg(prm.w2 + n) : 0.f;
+    else if (k < 32) v = n > 32 ? __ldg(prm.w3 + k * 63 + NRT_OB + (n - 33)) : 0.f;
+    else v = (k == 32 && n == 32) ? 1.0f : 0.f;
+    put_split_bw(bw, BW_B12 + ((k >> 2) * 48 + n) * 4 + (k & 3), v);
   }
   for (int i = t; i < 32 * 32; i += BWD_THREADS) {  // W1T[f][j] = w1[j][f]
     const int f = i >> 5, j = i & 31;
@@ -173,7 +172,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
   if (t < TC_THREADS) {
     scatter_warps(P, s_lv, ring, reinterpret_cast<float2*>(grads.grid), n_tiles);
   } else {
-  int k = 0;                      // tiles done by this CTA: ring stage = k & 1
+  int k = 0;                      // tiles done by this CTA
   for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++k) {
     const int64_t pt = tl * 128 + row;
     const bool active = pt < n_pts;
@@ -243,29 +242,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
       tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
       tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
     }
-    // ---- recompute layer 2: o = [sdf, geo] ----
-    run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W2 * 4, c.w_lo + FW_W2 * 4);
+    // ---- recompute phase 2 on [h1 | oneblob]: o = [sdf, geo] (columns 0..15) and a3 (columns 16..47) ----
+    run_layer<80, 48>(c, TA_X0, c.w_hi + FW_W23 * 4, c.w_lo + FW_W23 * 4);
     {
-      float o[8];
+      float o[8], a3[16];
       tmem_ld8(c.lane_tb + TC_ACC + 8 * half, o);
+      tmem_ld16(c.lane_tb + TC_ACC + 16 + 16 * half, a3);
       tmem_ld_wait();
-      float hi[8], lo[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        hi[k] = tf32_hi(o[k]);
-        lo[k] = o[k] - hi[k];
-        xcol[(XR_GEO + 8 * half + k) * 4] = hi[k];
-      }
-      tmem_st8(c.lane_tb + TC_AHI + TA_GEO + 8 * half, hi);
-      tmem_st8(c.lane_tb + TC_ALO + TA_GEO + 8 * half, lo);
-    }
-    // ---- recompute colour layer 1 ----
-    run_layer<64, 32>(c, TA_OB, c.w_hi + FW_W3 * 4, c.w_lo + FW_W3 * 4);
-    {
+      for (int k = 0; k < 8; ++k) xcol[(XR_GEO + 8 * half + k) * 4] = tf32_hi(o[k]);
       // h3 = relu(a3); dh3 = W4^T dc; da3 = dh3 * relu'
-      float a3[16];
-      tmem_ld16(c.lane_tb + TC_ACC + 16 * half, a3);
-      tmem_ld_wait();
       if (half == 0) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) ycol[(YR_DC + k) * 4] = tf32_hi(dc[k]);
@@ -284,30 +270,26 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
       }
       tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
       tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
-    }
-    // ---- d o = [dsdf, da3 W3[:, 48:63]] ----
-    run_layer<32, 16>(c, TA_X0, bw_hi + BW_W3G * 4, bw_lo + BW_W3G * 4);
-    {
-      float dg[8];
-      tmem_ld8(c.lane_tb + TC_ACC + 8 * half, dg);
-      tmem_ld_wait();
-      if (half == 0) dg[0] = dsdf;                      // column 0 of the accumulator is identically zero
-      float hi[8], lo[8];
+      if (half == 0) {
+        // the dsdf block [dsdf, 0 x 7] goes behind da3, into the first eight (now dead) OneBlob columns
+        float dh[8], dl[8];
+        dh[0] = tf32_hi(dsdf);
+        dl[0] = dsdf - dh[0];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        hi[i] = tf32_hi(dg[i]);
-        lo[i] = dg[i] - hi[i];
-        ycol[(YR_DO + 8 * half + i) * 4] = hi[i];
+        for (int i = 1; i < 8; ++i) dh[i] = dl[i] = 0.f;
+        tmem_st8(c.lane_tb + TC_AHI + TA_OB, dh);
+        tmem_st8(c.lane_tb + TC_ALO + TA_OB, dl);
       }
-      tmem_st8(c.lane_tb + TC_AHI + TA_GEO + 8 * half, hi);
-      tmem_st8(c.lane_tb + TC_ALO + TA_GEO + 8 * half, lo);
     }
-    // ---- dh1 = do W2 ----
-    run_layer<16, 32>(c, TA_GEO, bw_hi + BW_W2T * 4, bw_lo + BW_W2T * 4);
+    // ---- phase B12 on [da3 | dsdf]: dh1 (columns 0..31) and d o (columns 32..47) ----
+    run_layer<40, 48>(c, TA_X0, bw_hi + BW_B12 * 4, bw_lo + BW_B12 * 4);
     {
-      float dh[16];
+      float dh[16], dov[8];
       tmem_ld16(c.lane_tb + TC_ACC + 16 * half, dh);
+      tmem_ld8(c.lane_tb + TC_ACC + 32 + 8 * half, dov);
       tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ycol[(YR_DO + 8 * half + i) * 4] = tf32_hi(dov[i]);
       float hi[16], lo[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -346,9 +328,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
           reinterpret_cast<float4*>(dfeat + pt * NRT_ENC + 16 * half)[q] = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
       }
       // hand the tile to the scatter warps through the ring
-      const int st = k & 1;
-      float* stage = ring + st * RING_STAGE_FLOATS;
-      if (k >= RING_STAGES) bar_sync(BAR_EMPTY0 + st, BWD_THREADS);
+      float* stage = ring;
+      if (k >= 1) bar_sync(BAR_EMPTY, BWD_THREADS);
 #pragma unroll
       for (int q = 0; q < 4; ++q) sts4(stage + ((4 * half + q) * 128 + row) * 4, df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
       if (half == 0) {
@@ -358,7 +339,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
         xs[256 + row] = x2;
         xs[384 + row] = active ? 1.0f : 0.0f;
       }
-      bar_arrive(BAR_FULL0 + st, BWD_THREADS);
+      bar_arrive(BAR_FULL, BWD_THREADS);
     }
     // uncertainty grid: raw[...,4] is the trilinear sample itself
     if (half == 1 && active && grads.uncert && du != 0.f) {
@@ -403,7 +384,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
 }
 
 size_t decode_bwd_tc_smem() {
-  return TC_SMEM_WEIGHTS + (size_t)(2 * BW_FLOATS + 128 + XT_FLOATS + YT_FLOATS + RING_STAGES * RING_STAGE_FLOATS) * sizeof(float);
+  return TC_SMEM_WEIGHTS + (size_t)(2 * BW_FLOATS + 128 + XT_FLOATS + YT_FLOATS + RING_STAGE_FLOATS) * sizeof(float);
 }
 
 int launch_decode_bwd(const NrtPlan* plan, const NrtParams* prm, const PointSource& src, int64_t n_pts, const float* feat,

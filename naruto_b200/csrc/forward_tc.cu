@@ -11,10 +11,11 @@
 //                           integrated warp-per-ray with shuffle reductions (sdf2weights + raw2outputs).
 //
 // TMEM columns (256 allocated per CTA, two CTAs per SM):
-//   [0,32)    accumulator of the current layer
-//   [32,128)  A_hi: X0[32] (hash features, later relu(h1), later relu(h3)) | OneBlob[48] | geo[16]
-//   [128,224) A_lo: same structure, the low-order pieces
-// Layer 1 reads A columns X0|OneBlob (K=80), layer 2 reads X0 (K=32), layer 3 reads OneBlob|geo (K=64), layer 4 reads X0.
+//   [0,64)    accumulator of the current phase
+//   [64,144)  A_hi: X0[32] (hash features, later relu(h1), later relu(h3)) | OneBlob[48]
+//   [144,224) A_lo: same structure, the low-order pieces
+// Three dependent tensor-core phases per tile (layer fusion, mlp_tc.cuh): h1 from X0|OneBlob (K=80, N=32); o and a3
+// together from h1|OneBlob (K=80, N=48); rgb logits from relu(a3) in X0 (K=32, N=16).
 //
 // Reference semantics: tp/model/scene_rep.py:160-178 (run_network), src/slam/coslam/model/scene_rep.py:58-64,98-148
 // (calc_embedding / query_sdf / query_color_sdf), src/slam/coslam/model/decoder.py:29-41,99-116, and for the ray kernel
@@ -65,7 +66,7 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
     stage16(c, TA_OB + 16 * d, bins);
   }
   out.unc = (half == 1 && active) ? uncert_sample(P, ug, x0, x1, x2) : 0.f;
-  // ---- SDF net ----
+  // ---- phase 1: h1 = relu(W1 [hash | oneblob]) ----
   run_layer<80, 32>(c, TA_X0, c.w_hi + FW_W1 * 4, c.w_lo + FW_W1 * 4);
   {
     float h[16];
@@ -75,23 +76,17 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
     for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
     stage16(c, TA_X0 + 16 * half, h);
   }
-  run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W2 * 4, c.w_lo + FW_W2 * 4);
-  {
-    tmem_ld8(c.lane_tb + TC_ACC + 8 * half, out.o8);      // o[0] = sdf, o[1..15] = geo
-    tmem_ld_wait();
-    if (COLOR) stage8(c, TA_GEO + 8 * half, out.o8);
-  }
+  // ---- phase 2 on [h1 | oneblob]: o = W2 h1 (columns 0..15) and a3 = W23 h1 + W3_ob oneblob (columns 16..47) ----
+  run_layer<80, 48>(c, TA_X0, c.w_hi + FW_W23 * 4, c.w_lo + FW_W23 * 4);
+  tmem_ld8(c.lane_tb + TC_ACC + 8 * half, out.o8);        // o[0] = sdf, o[1..15] = geo
   if (COLOR) {
-    // ---- colour net ----
-    run_layer<64, 32>(c, TA_OB, c.w_hi + FW_W3 * 4, c.w_lo + FW_W3 * 4);
-    {
-      float h[16];
-      tmem_ld16(c.lane_tb + TC_ACC + 16 * half, h);
-      tmem_ld_wait();
+    float h[16];
+    tmem_ld16(c.lane_tb + TC_ACC + 16 + 16 * half, h);
+    tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
-      stage16(c, TA_X0 + 16 * half, h);
-    }
+    for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+    stage16(c, TA_X0 + 16 * half, h);
+    // ---- phase 3: rgb logits = W4 relu(a3) ----
     run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W4 * 4, c.w_lo + FW_W4 * 4);
     if (half == 0) {
       float r[4];
@@ -102,6 +97,7 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
       out.rgb[2] = r[2];
     }
   } else {
+    tmem_ld_wait();
     out.rgb[0] = out.rgb[1] = out.rgb[2] = 0.f;
   }
   // No barrier needed before the next tile: its tcgen05.st target only A columns whose last reader (this tile's MMAs)

@@ -12,22 +12,26 @@
 
 using namespace umma;
 
+// Layer fusion.  The SDF net's second layer has no activation, so the colour net's first layer can be folded onto h1:
+//     a3 = W3[:, :48] oneblob + W3[:, 48:63] geo,   geo = W2[1:16, :] h1   =>   a3 = W3[:, :48] oneblob + W23 h1,
+//     W23 = W3[:, 48:63] W2[1:16, :]  (32 x 32, formed once per CTA in fp32).
+// One tensor-core phase on A = [h1 | oneblob] (K = 80) therefore yields o = W2 h1 (16) and a3 (32) together (N = 48):
+// three dependent phases per forward tile instead of four, and the same trick merges two backward phases.
+//
 // shared-memory forward weight block (floats): chunk-major K-major B operands; the lo pieces follow at +FW_FLOATS
-#define FW_W1 0                   // [20 K-chunks][32 rows j][4]   k: hash 0..31 | oneblob 32..79
-#define FW_W2 (FW_W1 + 80 * 32)   // [ 8][16 rows i][4]            k: h1 0..31
-#define FW_W3 (FW_W2 + 32 * 16)   // [16][32 rows j][4]            k: oneblob 0..47 | 0 (sdf slot) | geo 49..63
-#define FW_W4 (FW_W3 + 64 * 32)   // [ 8][16 rows i][4]            rows 3..15 = 0
+#define FW_W1 0                    // [20 K-chunks][32 rows j][4]   k: hash 0..31 | oneblob 32..79
+#define FW_W23 (FW_W1 + 80 * 32)   // [20][48 rows][4]  k: h1 0..31 | oneblob 32..79; rows 0..15 = [W2 | 0], 16..47 = [W23 | W3_ob]
+#define FW_W4 (FW_W23 + 80 * 48)   // [ 8][16 rows i][4]            rows 3..15 = 0
 #define FW_FLOATS (FW_W4 + 32 * 16)
 
 // TMEM columns common to both kernels
-#define TC_ACC 0                  // [0,32)    accumulator of the current layer
-#define TC_AHI 32                 // [32,128)  A_hi: X0[32] | OneBlob[48] | o[16] = sdf (zero weight) + geo[15]
-#define TC_ALO 128                // [128,224) A_lo: same structure, the low-order pieces
+#define TC_ACC 0                   // [0,64)    accumulator of the current phase (up to N = 48)
+#define TC_AHI 64                  // [64,144)  A_hi: X0[32] (hash features, later relu(h1), relu(h3), ...) | OneBlob[48]
+#define TC_ALO 144                 // [144,224) A_lo: same structure, the low-order pieces
 #define TA_X0 0
 #define TA_OB 32
-#define TA_GEO 80
 
-#define TC_THREADS 256            // MLP threads per CTA (thread pairs of 128 rows)
+#define TC_THREADS 256             // MLP threads per CTA (thread pairs of 128 rows)
 #define TC_SMEM_HEADER 128
 #define TC_SMEM_WEIGHTS (TC_SMEM_HEADER + 2 * FW_FLOATS * 4)
 
@@ -37,19 +41,25 @@ __device__ __forceinline__ void put_split(float* hi_blk, int o, float v) {
   hi_blk[o + FW_FLOATS] = v - h;
 }
 
+// W23[j][m] = sum_g w3[j][48+g] * w2[1+g][m]
+__device__ __forceinline__ float w23_at(const NrtParams& prm, int j, int m) {
+  float acc = 0.f;
+#pragma unroll
+  for (int g = 0; g < NRT_GEO; ++g) acc = fmaf(__ldg(prm.w3 + j * 63 + NRT_OB + g), __ldg(prm.w2 + (1 + g) * 32 + m), acc);
+  return acc;
+}
+
 __device__ __forceinline__ void load_weights_tc(float* sw, const NrtParams& prm) {
   for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) {
     const int j = i / 80, k = i % 80;
     put_split(sw, FW_W1 + ((k >> 2) * 32 + j) * 4 + (k & 3), __ldg(prm.w1 + i));
   }
-  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
-    const int r = i >> 5, k = i & 31;
-    put_split(sw, FW_W2 + ((k >> 2) * 16 + r) * 4 + (k & 3), __ldg(prm.w2 + i));
-  }
-  for (int i = threadIdx.x; i < 32 * 64; i += blockDim.x) {
-    const int j = i >> 6, k = i & 63;
-    // the colour net reads [oneblob | geo]; its A columns are [oneblob | o] with o[0] = sdf, so column 48 gets weight 0
-    put_split(sw, FW_W3 + ((k >> 2) * 32 + j) * 4 + (k & 3), k < 48 ? __ldg(prm.w3 + j * 63 + k) : k == 48 ? 0.f : __ldg(prm.w3 + j * 63 + k - 1));
+  for (int i = threadIdx.x; i < 48 * 80; i += blockDim.x) {
+    const int n = i / 80, k = i % 80;
+    float v;
+    if (n < 16) v = k < 32 ? __ldg(prm.w2 + n * 32 + k) : 0.f;
+    else v = k < 32 ? w23_at(prm, n - 16, k) : __ldg(prm.w3 + (n - 16) * 63 + (k - 32));
+    put_split(sw, FW_W23 + ((k >> 2) * 48 + n) * 4 + (k & 3), v);
   }
   for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
     const int r = i >> 5, k = i & 31;
