@@ -100,6 +100,9 @@ int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
   d.n_d = cfg->n_samples_d;
   d.n_r = cfg->n_range_d;
   d.S = cfg->n_samples_d + cfg->n_range_d;
+  d.step_u = d.n_d > 1 ? (d.far_z - d.near_z) / (float)(d.n_d - 1) : 0.f;
+  d.step_r = d.n_r > 1 ? (d.range_d - (-d.range_d)) / (float)(d.n_r - 1) : 0.f;
+  d.step_n = d.n_r > 1 ? (d.far_z - d.near_z) / (float)(d.n_r - 1) : 0.f;
   p->sm_count = 148;
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) {

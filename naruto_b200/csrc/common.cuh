@@ -40,6 +40,10 @@ struct DevPlan {
   float sc_trunc;       // float32(sc_factor * trunc)
   float near_z, far_z, depth_trunc, range_d;
   int n_d, n_r, S;
+  // torch.linspace steps, float32((end - start) / (steps - 1)) formed in fp32 like the tensor op:
+  float step_u;         // uniform ladder   linspace(near, far, n_d)
+  float step_r;         // range ladder     linspace(-range_d, range_d, n_r)
+  float step_n;         // near/far ladder  linspace(near, far, n_r)   (rays without a depth measurement)
 };
 
 struct NrtPlan {
@@ -308,9 +312,8 @@ struct PointOut {
 // z (smem, length S) receives the sorted (and optionally jittered) depths.
 // torch.linspace semantics: step=(end-start)/(steps-1); i < steps/2 ? start+step*i : end-step*(steps-1-i)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
+__device__ __forceinline__ float linspace_at(float start, float end, float step, int steps, int i) {
   if (steps == 1) return start;
-  float step = __fdiv_rn(__fsub_rn(end, start), (float)(steps - 1));
   return i < steps / 2 ? __fadd_rn(start, __fmul_rn(step, (float)i)) : __fsub_rn(end, __fmul_rn(step, (float)(steps - 1 - i)));
 }
 
@@ -318,27 +321,33 @@ __device__ __forceinline__ void warp_sample_z(const DevPlan& P, float td, const 
                                               uint64_t seed, int64_t ray, float* __restrict__ z, int lane) {
   const int nd = P.n_d, nr = P.n_r, S = P.S;
   const bool invalid = td <= 0.0f;       // reference: z_samples[target_d <= 0] = linspace(near, far)
-  // near-surface ladder value j
+  // near-surface ladder value j (lane j holds it; n_r <= 32 is the common case, larger ladders recompute)
   auto near_val = [&](int j) -> float {
-    return invalid ? linspace_at(P.near_z, P.far_z, nr, j) : __fadd_rn(linspace_at(-P.range_d, P.range_d, nr, j), td);
+    return invalid ? linspace_at(P.near_z, P.far_z, P.step_n, nr, j)
+                   : __fadd_rn(linspace_at(-P.range_d, P.range_d, P.step_r, nr, j), td);
   };
+  const float my_near = lane < nr ? near_val(lane) : 3.4e38f;
   // stable merge by rank: uniform ladder first on ties
-  for (int i = lane; i < nd; i += 32) {
-    float v = linspace_at(P.near_z, P.far_z, nd, i);
+  for (int i = lane; i < nd + ((32 - nd % 32) % 32); i += 32) {       // all lanes iterate together (shuffles inside)
+    const float v = i < nd ? linspace_at(P.near_z, P.far_z, P.step_u, nd, i) : 0.f;
     int below = 0;
-    for (int j = 0; j < nr; ++j) below += near_val(j) < v ? 1 : 0;
-    z[i + below] = v;
+    if (nr <= 32) {
+      for (int j = 0; j < nr; ++j) below += __shfl_sync(0xffffffffu, my_near, j) < v ? 1 : 0;
+    } else {
+      for (int j = 0; j < nr; ++j) below += near_val(j) < v ? 1 : 0;
+    }
+    if (i < nd) z[i + below] = v;
   }
   for (int j = lane; j < nr; j += 32) {
-    float v = near_val(j);
+    const float v = near_val(j);
     int le = 0;
     if (nd > 0) {
       // count uniform samples <= v: guess from the spacing, then correct with the exact ladder values
-      float step = nd > 1 ? (P.far_z - P.near_z) / (float)(nd - 1) : 1.0f;
+      const float step = nd > 1 ? P.step_u : 1.0f;
       int g = (int)floorf((v - P.near_z) / step) + 1;
       g = max(0, min(nd, g));
-      while (g < nd && linspace_at(P.near_z, P.far_z, nd, g) <= v) ++g;
-      while (g > 0 && linspace_at(P.near_z, P.far_z, nd, g - 1) > v) --g;
+      while (g < nd && linspace_at(P.near_z, P.far_z, P.step_u, nd, g) <= v) ++g;
+      while (g > 0 && linspace_at(P.near_z, P.far_z, P.step_u, nd, g - 1) > v) --g;
       le = g;
     }
     z[j + le] = v;
@@ -379,7 +388,9 @@ __device__ __forceinline__ void warp_sample_z(const DevPlan& P, float td, const 
 
 // ---------------------------------------------------------------------------------------------
 // per-ray compositing by one warp (tp/model/scene_rep.py:64-84 + src/slam/coslam/model/scene_rep.py:66-96).
-// raw: smem [S][5], z: smem [S].  Every lane returns the same RayOut.
+// raw: smem [S][5], z: smem [S].  Every lane returns the same RayOut.  Lane l owns samples l, l+32, ...; the bell weight of
+// each owned sample is evaluated once and kept in registers, and the colour / uncertainty activations are only evaluated
+// for samples inside the truncation window (weight > 0).
 // ---------------------------------------------------------------------------------------------
 struct RayOut {
   float rgb[3], depth, depth_var, acc, disp, uncert;
@@ -387,13 +398,17 @@ struct RayOut {
   float z_cut;       // z_surf + sc*trunc
 };
 
+// sigma(a) * sigma(-a), a = sdf / trunc; even in a, evaluated as e / (1 + e)^2 with e = exp(-|a|) (no overflow)
 __device__ __forceinline__ float bell_weight(float sdf, float trunc) {
-  float a = __fdiv_rn(sdf, trunc);
-  return sigmoidf_(a) * sigmoidf_(-a);
+  const float a = __fdiv_rn(sdf, trunc);
+  const float e = expf(-fabsf(a));
+  const float d = 1.0f + e;
+  return __fdiv_rn(e, d * d);
 }
 
 __device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, const float* __restrict__ raw,
                                                  const float* __restrict__ z, float* __restrict__ w_out, int lane) {
+  constexpr int NP = NRT_SMAX / 32;
   // first sign change (argmax of the 0/1 mask -> 0 when there is none)
   int first = 0x7fffffff;
   for (int s = lane; s < S - 1; s += 32) {
@@ -406,22 +421,39 @@ __device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, 
   if (first == 0x7fffffff) first = 0;
   RayOut r;
   r.z_cut = __fadd_rn(z[first], P.sc_trunc);
+  float bw[NP], zv[NP];
   float ws = 0.f;
-  for (int s = lane; s < S; s += 32)
-    if (z[s] < r.z_cut) ws += bell_weight(raw[s * 5 + 3], P.trunc);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int s = p * 32 + lane;
+    bw[p] = 0.f;
+    zv[p] = 0.f;
+    if (s < S) {
+      zv[p] = z[s];
+      if (zv[p] < r.z_cut) bw[p] = bell_weight(raw[s * 5 + 3], P.trunc);
+      ws += bw[p];
+    }
+  }
   ws = warp_sum(ws);
   r.wsum = ws;
   const float denom = ws + 1e-8f;
   float c0 = 0, c1 = 0, c2 = 0, dep = 0, acc = 0, unc = 0;
-  for (int s = lane; s < S; s += 32) {
-    float w = z[s] < r.z_cut ? __fdiv_rn(bell_weight(raw[s * 5 + 3], P.trunc), denom) : 0.f;
-    if (w_out) w_out[s] = w;
-    c0 = fmaf(w, sigmoidf_(raw[s * 5 + 0]), c0);
-    c1 = fmaf(w, sigmoidf_(raw[s * 5 + 1]), c1);
-    c2 = fmaf(w, sigmoidf_(raw[s * 5 + 2]), c2);
-    dep = fmaf(w, z[s], dep);
-    acc += w;
-    unc = fmaf(w * w, softplusf_(raw[s * 5 + 4]) + 0.01f, unc);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int s = p * 32 + lane;
+    if (s < S) {
+      const float w = zv[p] < r.z_cut ? __fdiv_rn(bw[p], denom) : 0.f;
+      bw[p] = w;
+      if (w_out) w_out[s] = w;
+      if (w != 0.f) {
+        c0 = fmaf(w, sigmoidf_(raw[s * 5 + 0]), c0);
+        c1 = fmaf(w, sigmoidf_(raw[s * 5 + 1]), c1);
+        c2 = fmaf(w, sigmoidf_(raw[s * 5 + 2]), c2);
+        dep = fmaf(w, zv[p], dep);
+        acc += w;
+        unc = fmaf(w * w, softplusf_(raw[s * 5 + 4]) + 0.01f, unc);
+      }
+    }
   }
   r.rgb[0] = warp_sum(c0);
   r.rgb[1] = warp_sum(c1);
@@ -430,10 +462,13 @@ __device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, 
   r.acc = warp_sum(acc);
   r.uncert = warp_sum(unc);
   float var = 0.f;
-  for (int s = lane; s < S; s += 32) {
-    float w = z[s] < r.z_cut ? __fdiv_rn(bell_weight(raw[s * 5 + 3], P.trunc), denom) : 0.f;
-    float dz = z[s] - r.depth;
-    var = fmaf(w, dz * dz, var);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const int s = p * 32 + lane;
+    if (s < S) {
+      const float dz = zv[p] - r.depth;
+      var = fmaf(bw[p], dz * dz, var);
+    }
   }
   r.depth_var = warp_sum(var);
   r.disp = 1.0f / fmaxf(1e-10f, __fdiv_rn(r.depth, r.acc));
