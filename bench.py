@@ -189,8 +189,19 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     pg = None
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-        pg = dist.group.WORLD
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            pg = dist.group.WORLD
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     B, K, W = args.rays, args.steps, args.warmup
 
     cfg = replica_office0(n_samples_d=N_SAMPLES_D)
@@ -287,9 +298,12 @@ def run_ours(args):
                          f'{os.cpu_count()} host cpus)'}
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
     if rank != 0:
-        return
+        # destroy_process_group() blocks forever once NCCL collectives have been captured into CUDA graphs
+        # (measured on this pool, torch 2.11 / NCCL 2.28): leave without the teardown
+        sys.stdout.flush()
+        os._exit(0)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': 1e3 * t_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -306,6 +320,9 @@ def run_ours(args):
     if cpu is not None:
         line['cpu_baseline'] = cpu
     print(json.dumps(line))
+    if world > 1:
+        sys.stdout.flush()
+        os._exit(0)             # see above: no destroy_process_group() after graph-captured collectives
 
 
 def main():

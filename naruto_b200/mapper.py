@@ -88,7 +88,7 @@ class MappingStep:
         reduce_stats(self.stats, self.pg)
         p.loss_finalize(self.stats, self.losses); n += 1
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,
-                     self.G, workspace=self.ws_bwd); n += 3
+                     self.G, workspace=self.ws_bwd); n += 2
         if self.smooth_on and self.rank == 0:               # ray-independent term: added once, on rank 0
             p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
                              self.smooth_loss, self.G.grid, self.ws_smooth); n += 2
