@@ -284,12 +284,44 @@ def run_ours(args):
         kern = {k: {'ms': round(v[0], 4), 'algorithmic_GB_per_s': round(v[1] / v[0] / 1e6, 1)} for k, v in kt.items()}
         top = max(kt, key=lambda k: kt[k][0])
         ach = kt[top][1] / kt[top][0] / 1e6
+        traffic = None
+        tj = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tj):
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (same workload)
+            tr = json.load(open(tj))['dram_bytes_per_launch']
+            traffic = tr.get('decode_bwd_tc_kernel' if 'bwd' in top else 'render_fwd_tc_kernel')
         roof = {'bound': 'hbm', 'kernel': top, 'achieved': round(ach, 1), 'peak': hbm, 'unit': 'GB/s', 'frac': round(ach / hbm, 4),
-                'traffic': None, 'peak_source': how,
+                'traffic': traffic, 'peak_source': how,
                 'note': 'algorithmic bytes (SURVEY 8d) / CUDA-event time of the kernel launched alone, L2 flushed; at hash_size 16 '
-                        'the 6.5 MB table is L2-resident so the gather fraction is an accounting convention',
+                        'the 6.5 MB table is L2-resident so the gather fraction is an accounting convention; the backward entry '
+                        'is the launch pair composite_bwd_kernel (7% of it) + decode_bwd_tc_kernel, traffic is the latter\'s',
                 'hash_gather': {'kernel': 'render_fwd_tc_kernel', 'achieved': kern['render_fwd_tc_kernel']['algorithmic_GB_per_s'],
                                 'frac': round(kern['render_fwd_tc_kernel']['algorithmic_GB_per_s'] / hbm, 4)}}
+    sweep = None
+    if rank == 0 and world == 1 and args.sweep_rays > 0:
+        # BASELINE.json configs[4]: uncertainty-only forward sweep, 1M rays x 128 samples, no backward, only the per-ray
+        # depth / colour / uncertainty materialised (no raw / z_vals / saved features)
+        from naruto_b200.field import RenderBuffers
+        n_sw = args.sweep_rays
+        o, d, _, td = SyntheticFrame(OFFICE0_BOUND, seed=7).sample(n_sw)
+        o, d, td = o.to(dev), d.to(dev), td.to(dev)
+        sw_out = RenderBuffers(n_sw, S, dev, per_sample=False)
+        ts = []
+        for i in range(4):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            plan.render_fwd(ms.P, o, d, td, sw_out, perturb=1, seed=1234 + i)
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        t_sw = statistics.median(ts[1:])
+        hbm_sw, _ = peaks()
+        gbs = n_sw * BYTES_PER_RAY_FWD / t_sw / 1e6
+        sweep = {'workload': f'forward-only sweep, {n_sw} rays x {S} samples, outputs rgb/depth/uncert only, in-kernel Philox jitter',
+                 'ms': round(t_sw, 3), 'rays_per_s': n_sw / t_sw * 1e3, 'algorithmic_GB_per_s': round(gbs, 1),
+                 'frac_of_hbm_peak': round(gbs / hbm_sw, 4), 'finite': bool(torch.isfinite(sw_out.depth).all().item())}
+        del sw_out, o, d, td
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu, k_cpu = 1024, 5
         tot, threads = cpu_reference(n_cpu, k_cpu, 1)
@@ -317,6 +349,8 @@ def run_ours(args):
                 'ms_per_step': 1e3 * t_e2e / K},
         'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'kernels': kern, 'losses_finite': finite,
     }
+    if sweep is not None:
+        line['sweep'] = sweep
     if cpu is not None:
         line['cpu_baseline'] = cpu
     print(json.dumps(line))
@@ -333,6 +367,7 @@ def main():
     ap.add_argument('--rays', type=int, default=4096, help='rays per GPU per mapping iteration')
     ap.add_argument('--ref-rays', type=int, default=1024, help='rays per step for --impl reference')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--sweep-rays', type=int, default=1 << 20, help='rays of the forward-only sweep (0 = skip)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

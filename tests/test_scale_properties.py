@@ -1,0 +1,98 @@
+"""GPU: size-independent properties of the CUDA path at ragged and at full BASELINE sizes (the oracle is too slow there):
+the fused ray kernel against the point kernel + stand-alone compositor, linearity / accumulation of the backward pass,
+weight normalisation, empty inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _plan(n_samples_d, seed=3, grid_range=0.3):
+    from naruto_b200.configs import replica_office0, OFFICE0_BOUND
+    from naruto_b200.field import FieldPlan, FieldTensors
+    cfg = replica_office0(n_samples_d=n_samples_d)
+    plan = FieldPlan(cfg, OFFICE0_BOUND)
+    g = torch.Generator().manual_seed(seed)
+    lin = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / (i ** 0.5)).cuda()
+    P = FieldTensors(((torch.rand(plan.n_grid_floats, generator=g) * 2 - 1) * grid_range).cuda(), lin(32, 80), lin(16, 32),
+                     lin(32, 63), lin(3, 32), (3.0 + torch.rand(plan.uncert_dims, generator=g) * 2 - 1).cuda())
+    return cfg, plan, P
+
+
+def _rays(B, seed):
+    from naruto_b200.configs import OFFICE0_BOUND
+    from naruto_b200.synthetic import SyntheticFrame
+    o, d, rgb, td = SyntheticFrame(OFFICE0_BOUND, seed=seed).sample(B)
+    return o.cuda(), d.cuda(), rgb.cuda(), td.cuda()
+
+
+@pytest.mark.parametrize('n_samples_d,B', [(32, 1), (32, 5), (32, 301), (117, 3), (117, 130), (189, 7), (245, 2)])
+def test_ray_kernel_equals_point_kernel_plus_compositor(n_samples_d, B):
+    """render_fwd (fused) == decode_fwd on the same points followed by composite_fwd: same tensor-core tiles, so bit-exact
+    `raw`; the per-ray outputs go through the same warp compositor."""
+    from naruto_b200.field import RenderBuffers
+    cfg, plan, P = _plan(n_samples_d)
+    S = plan.S
+    o, d, rgb, td = _rays(B, seed=B + S)
+    u = torch.rand(B, S, generator=torch.Generator().manual_seed(1)).cuda()
+    out = RenderBuffers(B, S, 'cuda', per_sample=True, weights=True, feat=True)
+    plan.render_fwd(P, o, d, td, out, u=u)
+    z = out.z_vals
+    assert torch.all(z[:, 1:] >= z[:, :-1]), 'z_vals must be sorted'
+    b = plan.bound.cuda()
+    pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
+    x = ((pts - b[:, 0]) / (b[:, 1] - b[:, 0])).reshape(-1, 3).contiguous()
+    raw, _, _ = plan.decode_fwd(P, x, with_color=True)
+    assert torch.equal(raw.view(B, S, 5), out.raw), (raw.view(B, S, 5) - out.raw).abs().max()
+    assert torch.equal(plan.encode_fwd(P.grid, x), out.feat)
+    comp = plan.composite_fwd(out.raw, z)
+    for k in ('rgb', 'depth', 'depth_var', 'acc', 'disp', 'uncert', 'weights'):
+        assert torch.equal(getattr(comp, k), getattr(out, k)), k
+    torch.cuda.synchronize()
+    w = out.weights
+    assert torch.isfinite(out.rgb).all() and (w >= 0).all()
+    assert torch.allclose(w.sum(1), out.acc, atol=1e-5) and (out.acc <= 1.0 + 1e-5).all()
+
+
+def test_empty_inputs():
+    from naruto_b200.field import RenderBuffers
+    cfg, plan, P = _plan(32)
+    e3 = torch.empty(0, 3, device='cuda')
+    out = RenderBuffers(0, plan.S, 'cuda')
+    plan.render_fwd(P, e3, e3, torch.empty(0, device='cuda'), out)
+    raw, _, _ = plan.decode_fwd(P, e3)
+    assert raw.shape == (0, 5)
+    assert plan.encode_fwd(P.grid, e3).shape == (0, 32)
+    torch.cuda.synchronize()
+
+
+def test_backward_linearity_and_accumulation_at_bench_size():
+    """4096 rays x 128 samples (the bench workload): d(2L) = 2 dL and two backward calls accumulate, for every parameter
+    tensor; checked at the level the atomics' summation order allows."""
+    from naruto_b200.field import FieldTensors, RenderBuffers
+    cfg, plan, P = _plan(117, grid_range=0.05)
+    B, S = 4096, plan.S
+    o, d, rgb, td = _rays(B, seed=9)
+    out = RenderBuffers(B, S, 'cuda', per_sample=True, feat=True)
+    plan.render_fwd(P, o, d, td, out, perturb=0)
+    stats = plan.new_stats('cuda')
+    losses = torch.zeros(8, device='cuda')
+    plan.loss_partial(out, rgb, td, stats)
+    plan.loss_finalize(stats, losses)
+    assert torch.isfinite(losses[:6]).all()
+    lg = torch.tensor([5.0, 0.1, 1000.0, 10.0, 0.005], device='cuda')
+
+    def grads(scale, calls):
+        G = FieldTensors(*[torch.zeros_like(t) for t in P.as_list()])
+        for _ in range(calls):
+            plan.render_bwd(P, o, d, rgb, td, out, stats, lg * scale, G)
+        torch.cuda.synchronize()
+        return G
+
+    g1, g2, gacc = grads(1.0, 1), grads(2.0, 1), grads(1.0, 2)
+    for name, a, b, c in zip(('grid', 'w1', 'w2', 'w3', 'w4', 'uncert'), g1.as_list(), g2.as_list(), gacc.as_list()):
+        s = a.abs().max().item()
+        assert s > 0, name
+        tol = 2e-3 if name.startswith('w') else 1e-4        # weight gradients: single-pass TF32 contraction over points
+        assert (2 * a - b).abs().max().item() <= tol * 2 * s, name
+        assert (2 * a - c).abs().max().item() <= tol * 2 * s, name
