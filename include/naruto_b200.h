@@ -26,6 +26,9 @@
  *                             through the modules above
  *   nrt_smooth_fwd_bwd        CoSLAM.smoothness + its backward (tp/coslam.py:245-269)
  *   nrt_adam_step             torch.optim.Adam as configured at src/slam/coslam/coslam.py:409-419,240-243
+ *   nrt_camera_rays .. nrt_active_select   the per-iteration ray sampling of global_BA (src/slam/coslam/coslam.py:302-359),
+ *                             KeyFrameDatabase (tp/model/keyframe.py, src/slam/coslam/model/keyframe.py) and ActiveRaySampler
+ *                             (src/slam/coslam/active_ray_sampler.py)
  */
 #ifndef NARUTO_B200_H
 #define NARUTO_B200_H
@@ -214,6 +217,38 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   const int32_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int zero_grad, void* stream);
 int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream);
+
+/* ---- device-resident ray sampling ----------------------------------------------------------------
+ * The host half of the mapping iteration on device-resident data.  Index lists are dev int64
+ * arrays: either the reference's own `random.sample` draws (parity) or the output of nrt_sample_indices. */
+/* get_camera_rays, type 'OpenGL' (tp/datasets/utils.py:24-57): dirs dev [H,W,3] = [(i-cx)/fx, -(j-cy)/fy, -1] */
+int nrt_camera_rays(int32_t H, int32_t W, float fx, float fy, float cx, float cy, float* dirs, void* stream);
+/* cat([direction, rgb, depth[...,None]], -1).reshape(-1, 7) (src/slam/coslam/coslam.py:290-291; keyframe.py:43-44) */
+int nrt_pack_frame(const float* direction, const float* rgb, const float* depth, int64_t n_pixels, float* frame_rays, void* stream);
+/* count (dev int32, overwritten) of pixels with 0 < depth <= depth_trunc (src/slam/coslam/coslam.py:319-321) */
+int nrt_valid_depth_count(const float* frame_rays, int64_t n_pixels, float depth_trunc, int32_t* count, void* stream);
+/* KeyFrameDatabaseNaruto.add_keyframe (src/slam/coslam/model/keyframe.py:21-60): slot[i] = frame_rays[idxs[i % n_idx]]
+ * for i < rays_per_kf (the reference doubles the selected rows until there are enough of them) */
+int nrt_kf_store(const float* frame_rays, const int64_t* idxs, int64_t n_idx, int32_t rays_per_kf, float* slot, void* stream);
+/* random.sample(range(n), k): k distinct uniform indices (a keyed bijection of [0,n), seed-deterministic).  If n_dev != NULL
+ * the population size is read from that device int32 (e.g. the valid-depth count), otherwise `n` is used. */
+int nrt_sample_indices(int64_t n, const int32_t* n_dev, int64_t k, uint64_t seed, int64_t* out, void* stream);
+/* KeyFrameDatabase.sample_global_rays (tp/model/keyframe.py:69-79) + the batch assembly and pose transform of global_BA
+ * (src/slam/coslam/coslam.py:329-344).  kf_rays dev [num_kf*rays_per_kf,7]; frame_ids dev int64 [num_kf]; poses dev
+ * [n_poses,4,4] whose last row is the current frame.  Outputs dev [n_global+n_cur, 3|3|3|1]. */
+int nrt_assemble_rays(const float* kf_rays, const int64_t* frame_ids, int32_t rays_per_kf, int32_t keyframe_every,
+                      const int64_t* idxs_global, int64_t n_global, const float* cur_rays, const int64_t* idx_cur, int64_t n_cur,
+                      const float* poses, int32_t n_poses, float* rays_o, float* rays_d, float* target_s, float* target_d,
+                      void* stream);
+/* ActiveRaySampler.sample_rays (src/slam/coslam/active_ray_sampler.py:77-149): out = [the num_uncert_sample pool rays with the
+ * LOWEST cached uncertainty (ascending pool order; ties at the threshold broken by lowest index) | rows 0 .. base-K | the
+ * last ceil(n_cur/mul) rows], out_* dev [base + ceil(n_cur/mul), .].  vol_dims, bound_min: HOST arrays of 3.  chosen: dev
+ * int32 [K] pool indices or NULL.  workspace: dev scratch of nrt_active_select_workspace(n_rays) bytes. */
+int64_t nrt_active_select_workspace(int64_t n_rays);
+int nrt_active_select(const float* rays_o, const float* rays_d, const float* target_s, const float* target_d, int64_t n_rays,
+                      int64_t n_cur, const float* uncert_vol, const int32_t* vol_dims, const float* bound_min, int32_t base_sample_num,
+                      int32_t num_uncert_sample, int32_t oversample_mul, float* out_o, float* out_d, float* out_s, float* out_t,
+                      int32_t* chosen, void* workspace, void* stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------- */
 /* Tensor-core self-test (no reference counterpart): one CTA multiplies small fp32 matrices through the same

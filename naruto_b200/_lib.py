@@ -72,6 +72,16 @@ SIGNATURES = {
     'nrt_smooth_fwd_bwd': (C.c_int, [_P, c_fp, c_fp, C.c_int32, C.c_double, C.c_double, c_f, c_fp, c_fp, c_fp, _P]),
     'nrt_adam_step': (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_int32, c_fp, c_f, c_f, c_f, c_f, c_f, C.c_int, _P]),
     'nrt_counter_add': (C.c_int, [c_fp, C.c_int32, _P]),
+    'nrt_camera_rays': (C.c_int, [C.c_int32, C.c_int32, c_f, c_f, c_f, c_f, c_fp, _P]),
+    'nrt_pack_frame': (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, c_fp, _P]),
+    'nrt_valid_depth_count': (C.c_int, [c_fp, C.c_int64, c_f, c_fp, _P]),
+    'nrt_kf_store': (C.c_int, [c_fp, c_fp, C.c_int64, C.c_int32, c_fp, _P]),
+    'nrt_sample_indices': (C.c_int, [C.c_int64, c_fp, C.c_int64, C.c_uint64, c_fp, _P]),
+    'nrt_assemble_rays': (C.c_int, [c_fp, c_fp, C.c_int32, C.c_int32, c_fp, C.c_int64, c_fp, c_fp, C.c_int64, c_fp, C.c_int32,
+                                    c_fp, c_fp, c_fp, c_fp, _P]),
+    'nrt_active_select_workspace': (C.c_int64, [C.c_int64]),
+    'nrt_active_select': (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_int64, c_fp, C.POINTER(C.c_int32), C.POINTER(c_f),
+                                    C.c_int32, C.c_int32, C.c_int32, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _P]),
     'nrt_selftest_umma_raw': (C.c_int, [c_fp, C.c_int32, c_fp, C.c_int32] + [C.c_int32] * 10 + [c_fp, _P]),
     'nrt_selftest_umma': (C.c_int, [C.c_int, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int, c_fp, _P]),
 }

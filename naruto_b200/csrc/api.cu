@@ -29,6 +29,15 @@ int launch_smooth(const NrtPlan*, const float*, const float*, int, double, doubl
 int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
                 cudaStream_t);
 int launch_counter_add(int*, int, cudaStream_t);
+int launch_camera_rays(int, int, float, float, float, float, float*, cudaStream_t);
+int launch_pack_frame(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
+int launch_valid_depth_count(const float*, int64_t, float, int*, cudaStream_t);
+int launch_kf_store(const float*, const int64_t*, int64_t, int, float*, cudaStream_t);
+int launch_feistel_sample(int64_t, int64_t, uint64_t, const int*, int64_t*, cudaStream_t);
+int launch_assemble_rays(const float*, const int64_t*, int, int, const int64_t*, int64_t, const float*, const int64_t*, int64_t,
+                         const float*, int, float*, float*, float*, float*, cudaStream_t);
+int launch_active_select(const float*, const float*, const float*, const float*, int64_t, int64_t, const float*, int, int, int,
+                         const float*, int, int, int, float*, float*, float*, float*, int*, void*, cudaStream_t);
 int launch_umma_selftest(int, const float*, const float*, int, int, int, float*, cudaStream_t);
 int launch_umma_raw(const float*, int, const float*, int, int, int, int, int, int, int, int, int, int, int, float*, cudaStream_t);
 
@@ -266,6 +275,58 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream) {
   NRT_REQUIRE(counter_dev, "null counter");
   return launch_counter_add(counter_dev, delta, (cudaStream_t)stream);
+}
+
+/* ---- device-resident ray sampling ---- */
+int nrt_camera_rays(int32_t H, int32_t W, float fx, float fy, float cx, float cy, float* dirs, void* stream) {
+  NRT_REQUIRE(H > 0 && W > 0 && dirs && fx != 0.f && fy != 0.f, "camera_rays arguments");
+  return launch_camera_rays(H, W, fx, fy, cx, cy, dirs, (cudaStream_t)stream);
+}
+
+int nrt_pack_frame(const float* direction, const float* rgb, const float* depth, int64_t n_pixels, float* frame_rays, void* stream) {
+  NRT_REQUIRE(n_pixels >= 0 && (n_pixels == 0 || (direction && rgb && depth && frame_rays)), "pack_frame arguments");
+  return launch_pack_frame(direction, rgb, depth, n_pixels, frame_rays, (cudaStream_t)stream);
+}
+
+int nrt_valid_depth_count(const float* frame_rays, int64_t n_pixels, float depth_trunc, int32_t* count, void* stream) {
+  NRT_REQUIRE(n_pixels >= 0 && count && (n_pixels == 0 || frame_rays), "valid_depth_count arguments");
+  return launch_valid_depth_count(frame_rays, n_pixels, depth_trunc, count, (cudaStream_t)stream);
+}
+
+int nrt_kf_store(const float* frame_rays, const int64_t* idxs, int64_t n_idx, int32_t rays_per_kf, float* slot, void* stream) {
+  NRT_REQUIRE(frame_rays && idxs && slot && n_idx > 0 && rays_per_kf > 0, "kf_store arguments");
+  return launch_kf_store(frame_rays, idxs, n_idx, rays_per_kf, slot, (cudaStream_t)stream);
+}
+
+int nrt_sample_indices(int64_t n, const int32_t* n_dev, int64_t k, uint64_t seed, int64_t* out, void* stream) {
+  NRT_REQUIRE(k >= 0 && (k == 0 || out) && (n_dev || n > 0), "sample_indices arguments");
+  return launch_feistel_sample(n, k, seed, n_dev, out, (cudaStream_t)stream);
+}
+
+int nrt_assemble_rays(const float* kf_rays, const int64_t* frame_ids, int32_t rays_per_kf, int32_t keyframe_every,
+                      const int64_t* idxs_global, int64_t n_global, const float* cur_rays, const int64_t* idx_cur, int64_t n_cur,
+                      const float* poses, int32_t n_poses, float* rays_o, float* rays_d, float* target_s, float* target_d,
+                      void* stream) {
+  NRT_REQUIRE(n_global >= 0 && n_cur >= 0 && rays_per_kf > 0 && keyframe_every > 0 && n_poses > 0 && poses, "assemble_rays arguments");
+  NRT_REQUIRE(n_global == 0 || (kf_rays && frame_ids && idxs_global), "assemble_rays: global part");
+  NRT_REQUIRE(n_cur == 0 || (cur_rays && idx_cur), "assemble_rays: current part");
+  NRT_REQUIRE(n_global + n_cur == 0 || (rays_o && rays_d && target_s && target_d), "assemble_rays outputs");
+  return launch_assemble_rays(kf_rays, frame_ids, rays_per_kf, keyframe_every, idxs_global, n_global, cur_rays, idx_cur, n_cur, poses,
+                              n_poses, rays_o, rays_d, target_s, target_d, (cudaStream_t)stream);
+}
+
+int64_t nrt_active_select_workspace(int64_t n_rays) { return n_rays > 0 ? n_rays * (int64_t)sizeof(uint32_t) : 0; }
+
+int nrt_active_select(const float* rays_o, const float* rays_d, const float* target_s, const float* target_d, int64_t n_rays,
+                      int64_t n_cur, const float* uncert_vol, const int32_t* vol_dims, const float* bound_min, int32_t base_sample_num,
+                      int32_t num_uncert_sample, int32_t oversample_mul, float* out_o, float* out_d, float* out_s, float* out_t,
+                      int32_t* chosen, void* workspace, void* stream) {
+  NRT_REQUIRE(rays_o && rays_d && target_s && target_d && uncert_vol && vol_dims && bound_min && out_o && out_d && out_s && out_t &&
+                  workspace && n_rays > 0 && n_cur >= 0 && oversample_mul > 0,
+              "active_select arguments");
+  return launch_active_select(rays_o, rays_d, target_s, target_d, n_rays, n_cur, uncert_vol, vol_dims[0], vol_dims[1], vol_dims[2],
+                              bound_min, base_sample_num, num_uncert_sample, oversample_mul, out_o, out_d, out_s, out_t, chosen,
+                              workspace, (cudaStream_t)stream);
 }
 
 int nrt_selftest_umma(int mode, const float* a, const float* b, int32_t k, int32_t n, int passes, float* d, void* stream) {

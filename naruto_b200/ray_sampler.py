@@ -1,0 +1,207 @@
+"""Device-resident ray sampling for the mapping iteration: host-side mirrors of the reference's
+`KeyFrameDatabaseNaruto` (src/slam/coslam/model/keyframe.py:21-60 on third_parties/coslam/model/keyframe.py:5-98) and
+`ActiveRaySampler` (src/slam/coslam/active_ray_sampler.py:36-149), plus `sample_mapping_batch`, the per-iteration sampling
+block of `CoSLAMNaruto.global_BA` (src/slam/coslam/coslam.py:302-359) as five kernel launches on device-resident data.
+
+The reference keeps the key-frame rays in a CPU tensor, draws indices with Python's `random.sample`, boolean-indexes the
+816 000-pixel current frame on the CPU every iteration and round-trips the ray end points through numpy for the
+uncertainty lookup.  Here the database (`[num_kf, rays_per_kf, 7]` fp32, the reference's layout), the current frame, the
+poses and the cached uncertainty volume live in HBM; indices are either passed in (the reference's own draws: parity
+tests) or generated on the device (`nrt_sample_indices`, a keyed bijection = a draw without replacement).
+
+All work is done by libnaruto_b200.so; there is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, dev):
+    return torch.as_tensor(t, dtype=torch.float32).to(dev).contiguous()
+
+
+def _i64(t, dev):
+    return torch.as_tensor(t, dtype=torch.int64).to(dev).contiguous()
+
+
+def camera_rays(H, W, fx, fy, cx, cy, device):
+    """get_camera_rays(H, W, fx, fy, cx, cy) of third_parties/coslam/datasets/utils.py:24-57 -> [H, W, 3] on `device`."""
+    lib = L.load()
+    out = torch.empty(H, W, 3, dtype=torch.float32, device=device)
+    L.check(lib.nrt_camera_rays(H, W, float(fx), float(fy), float(cx), float(cy), L.ptr(out), _stream()))
+    return out
+
+
+def pack_frame(direction, rgb, depth):
+    """[H*W, 7] = (direction 3, rgb 3, depth 1) from the three images of a batch (device tensors)."""
+    lib = L.load()
+    dev = direction.device
+    d, c, z = _f32(direction, dev).reshape(-1, 3), _f32(rgb, dev).reshape(-1, 3), _f32(depth, dev).reshape(-1)
+    out = torch.empty(d.shape[0], 7, dtype=torch.float32, device=dev)
+    L.check(lib.nrt_pack_frame(L.ptr(d), L.ptr(c), L.ptr(z), d.shape[0], L.ptr(out), _stream()))
+    return out
+
+
+def valid_depth_count(frame_rays, depth_trunc):
+    """Device int32[1]: number of rays with 0 < depth <= depth_trunc (stays on the device; no sync)."""
+    lib = L.load()
+    cnt = torch.zeros(1, dtype=torch.int32, device=frame_rays.device)
+    L.check(lib.nrt_valid_depth_count(L.ptr(frame_rays), frame_rays.shape[0], float(depth_trunc), L.ptr(cnt), _stream()))
+    return cnt
+
+
+def sample_indices(n, k, seed, device, n_dev=None):
+    """k distinct uniform indices of range(n) as a device int64 tensor.  n_dev: device int32[1] population size (then `n` is
+    ignored) -- lets the valid-depth count stay on the device."""
+    lib = L.load()
+    out = torch.empty(k, dtype=torch.int64, device=device)
+    L.check(lib.nrt_sample_indices(int(n), L.ptr(n_dev), int(k), int(seed) & 0xFFFFFFFFFFFFFFFF, L.ptr(out), _stream()))
+    return out
+
+
+class DeviceKeyFrameDatabase:
+    """KeyFrameDatabaseNaruto with the ray table in HBM.  Same constructor and method names; `idxs=` lets a caller pass the
+    index draw the reference would have made."""
+
+    def __init__(self, config, H, W, num_kf, num_rays_to_save, device):
+        self.config = config
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise L.NrtError('DeviceKeyFrameDatabase needs a CUDA device -- there is no CPU path')
+        self.lib = L.load()
+        self.rays = torch.zeros((num_kf, num_rays_to_save, 7), dtype=torch.float32, device=self.device)
+        self.num_rays_to_save = int(num_rays_to_save)
+        self.frame_ids = None                      # device int64 [n], like the reference's CPU tensor
+        self.H, self.W = H, W
+        self._n = 0
+        self._seed = int(config.get('seed', 0)) if isinstance(config, dict) else 0
+
+    def __len__(self):
+        return self._n
+
+    def get_length(self):
+        return self._n
+
+    def _next_seed(self):
+        self._seed += 0x9E3779B97F4A7C15
+        return self._seed
+
+    def attach_ids(self, frame_ids):
+        frame_ids = _i64(frame_ids, self.device).reshape(-1)
+        self.frame_ids = frame_ids if self.frame_ids is None else torch.cat([self.frame_ids, frame_ids], dim=0)
+        self._n = int(self.frame_ids.shape[0])
+
+    def add_keyframe(self, batch, filter_depth=False, idxs=None):
+        """src/slam/coslam/model/keyframe.py:38-60.  batch: direction [1,H,W,3], rgb [1,H,W,3], depth [1,H,W], frame_id."""
+        dev = self.device
+        frame = pack_frame(batch['direction'].to(dev), batch['rgb'].to(dev), batch['depth'].to(dev))
+        P = self.num_rays_to_save
+        if idxs is None:
+            if filter_depth:
+                cnt = valid_depth_count(frame, self.config['cam']['depth_trunc'])
+                # the reference draws min(num_valid, P) indices; drawing P from a smaller population repeats indices, which is
+                # what its doubling rule produces as well
+                idxs = sample_indices(0, P, self._next_seed(), dev, n_dev=cnt)
+                n_valid = None
+            else:
+                idxs = sample_indices(self.H * self.W, P, self._next_seed(), dev)
+                n_valid = None
+        else:
+            idxs = _i64(idxs, dev)
+            n_valid = idxs.shape[0]
+        frame_id = batch['frame_id']
+        self.attach_ids(frame_id if isinstance(frame_id, torch.Tensor) else torch.tensor([frame_id]))
+        if n_valid == 0:
+            return
+        slot = self.rays[self._n - 1]
+        L.check(self.lib.nrt_kf_store(L.ptr(frame), L.ptr(idxs), idxs.shape[0], P, L.ptr(slot), _stream()))
+
+    def sample_global_rays(self, bs, idxs=None):
+        """third_parties/coslam/model/keyframe.py:69-79 -> (rays [bs,7], frame_ids [bs]) device tensors."""
+        n = self._n * self.num_rays_to_save
+        if idxs is None:
+            idxs = sample_indices(n, bs, self._next_seed(), self.device)
+        else:
+            idxs = _i64(idxs, self.device)
+        rays = self.rays[:self._n].reshape(-1, 7)[idxs]           # plain gather: API parity only, the fused path below
+        return rays, self.frame_ids[idxs // self.num_rays_to_save]  # (sample_mapping_batch) never materialises this
+
+
+class DeviceActiveRaySampler:
+    """ActiveRaySampler.sample_rays on the device (same constructor / call signature)."""
+
+    def __init__(self, config=None, num_uncert_sample=500, oversample_mul=4):
+        self.num_uncert_sample = int(num_uncert_sample)
+        self.oversample_mul = int(oversample_mul)
+        self.base_sample_num = int(config['mapping']['sample'])
+        self.oversample_num = self.base_sample_num * self.oversample_mul
+        self.min_pixels_cur = int(config['mapping']['min_pixels_cur']) * self.oversample_mul
+        self.lib = L.load()
+        self.last_chosen = None
+
+    def sample_rays(self, rays_o, rays_d, target_s, target_d, idx_cur, uncert_vol, bbox, want_chosen=False):
+        """idx_cur: the list of current-frame indices (only its length is used, like the reference) or that length."""
+        dev = rays_o.device
+        n_cur = int(idx_cur) if isinstance(idx_cur, int) else len(idx_cur)
+        o, d, s, t = (_f32(x, dev) for x in (rays_o, rays_d, target_s, target_d))
+        N = o.shape[0]
+        vol = _f32(uncert_vol, dev)
+        tail = -(-n_cur // self.oversample_mul)
+        n_out = self.base_sample_num + tail
+        out_o, out_d, out_s = (torch.empty(n_out, 3, dtype=torch.float32, device=dev) for _ in range(3))
+        out_t = torch.empty(n_out, 1, dtype=torch.float32, device=dev)
+        chosen = torch.empty(self.num_uncert_sample, dtype=torch.int32, device=dev) if want_chosen else None
+        ws = torch.empty(max(self.lib.nrt_active_select_workspace(N) // 4, 1), dtype=torch.int32, device=dev)
+        dims = (C.c_int32 * 3)(*vol.shape)
+        bmin = (L.c_f * 3)(*[float(torch.tensor(b[0], dtype=torch.float32)) for b in bbox])
+        L.check(self.lib.nrt_active_select(L.ptr(o), L.ptr(d), L.ptr(s), L.ptr(t.reshape(-1)), N, n_cur, L.ptr(vol), dims, bmin,
+                                           self.base_sample_num, self.num_uncert_sample, self.oversample_mul, L.ptr(out_o),
+                                           L.ptr(out_d), L.ptr(out_s), L.ptr(out_t), L.ptr(chosen), L.ptr(ws), _stream()))
+        self.last_chosen = chosen
+        return out_o, out_d, out_s, out_t
+
+
+def sample_mapping_batch(kfdb, current_rays, poses_all, config, cached_uncert, bbox, sampler=None, idxs_global=None, idx_cur=None,
+                         seed=0):
+    """The sampling block of one global_BA iteration (src/slam/coslam/coslam.py:302-359), entirely on the device.
+
+    kfdb: DeviceKeyFrameDatabase; current_rays: [H*W,7] device tensor (pack_frame); poses_all: [n_kf+1,4,4] device tensor
+    whose last row is the current frame; sampler: DeviceActiveRaySampler or None (mapping.active_ray False).
+    idxs_global / idx_cur: the reference's draws (parity) or None (generated on the device; then NO host synchronisation
+    happens anywhere in this function).  Returns rays_o, rays_d, target_s, target_d of the iteration's batch."""
+    lib, dev = kfdb.lib, kfdb.device
+    if sampler is not None:
+        sample_num, min_pixels_cur = sampler.oversample_num, sampler.min_pixels_cur
+    else:
+        sample_num, min_pixels_cur = int(config['mapping']['sample']), int(config['mapping']['min_pixels_cur'])
+    num_cur = max(sample_num // len(kfdb), min_pixels_cur)
+    if idxs_global is None:
+        idxs_global = sample_indices(len(kfdb) * kfdb.num_rays_to_save, sample_num, seed * 2 + 1, dev)
+    else:
+        idxs_global = _i64(idxs_global, dev)
+    if idx_cur is None:
+        if config['mapping'].get('filter_depth', False):
+            cnt = valid_depth_count(current_rays, config['cam']['depth_trunc'])
+            idx_cur = sample_indices(0, num_cur, seed * 2 + 2, dev, n_dev=cnt)
+        else:
+            idx_cur = sample_indices(current_rays.shape[0], num_cur, seed * 2 + 2, dev)
+    else:
+        idx_cur = _i64(idx_cur, dev)
+    n_g, n_c = idxs_global.shape[0], idx_cur.shape[0]
+    N = n_g + n_c
+    poses = _f32(poses_all, dev)
+    o, d, s = (torch.empty(N, 3, dtype=torch.float32, device=dev) for _ in range(3))
+    t = torch.empty(N, 1, dtype=torch.float32, device=dev)
+    L.check(lib.nrt_assemble_rays(L.ptr(kfdb.rays), L.ptr(kfdb.frame_ids), kfdb.num_rays_to_save,
+                                  int(config['mapping']['keyframe_every']), L.ptr(idxs_global), n_g, L.ptr(current_rays),
+                                  L.ptr(idx_cur), n_c, L.ptr(poses), poses.shape[0], L.ptr(o), L.ptr(d), L.ptr(s), L.ptr(t),
+                                  _stream()))
+    if sampler is None:
+        return o, d, s, t
+    return sampler.sample_rays(o, d, s, t, n_c, cached_uncert, bbox)
