@@ -154,6 +154,14 @@ int nrt_oneblob_bwd(const NrtPlan* plan, const float* x, int64_t n, const float*
 int nrt_decode_fwd(const NrtPlan* plan, const NrtParams* params, const float* x, int64_t n, int with_color,
                    float* raw, float* sdf_uncert, float* geo, void* stream);
 
+/* get_map_volumes (src/slam/coslam/coslam_utils.py:58-97): the dense sweep the planner consumes.  dims: HOST int32[3] =
+ * lattice points per axis (getVoxels: round(extent/voxel + 0.0005) + 1); the lattice is torch.linspace over the plan's
+ * bound per axis, meshgrid 'ij'.  vol_sdf dev [d0,d1,d2]; vol_uncert dev [d0,d1,d2] = softplus(uncert)+0.01 where
+ * 0 <= sdf < 0.5, else 0.  One launch: lattice generation, encode, SDF net and masking fused; the reference's discarded
+ * `embed` pass is not reproduced. */
+int nrt_map_volumes(const NrtPlan* plan, const NrtParams* params, const int32_t* dims, float* vol_uncert, float* vol_sdf,
+                    void* stream);
+
 /* ---- rays ------------------------------------------------------------------------------------ */
 /* z_vals: dev [B,S].  u: dev [B,S] uniform draws (the reference's torch.rand) or NULL;
  * when u == NULL and perturb != 0 the kernel draws its own Philox stream from `seed`. */

@@ -29,6 +29,7 @@ int launch_smooth(const NrtPlan*, const float*, const float*, int, double, doubl
 int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
                 cudaStream_t);
 int launch_counter_add(int*, int, cudaStream_t);
+int launch_map_volumes(const NrtPlan*, const NrtParams*, const int*, float*, float*, cudaStream_t);
 int launch_camera_rays(int, int, float, float, float, float, float*, cudaStream_t);
 int launch_pack_frame(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
 int launch_valid_depth_count(const float*, int64_t, float, int*, cudaStream_t);
@@ -275,6 +276,12 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream) {
   NRT_REQUIRE(counter_dev, "null counter");
   return launch_counter_add(counter_dev, delta, (cudaStream_t)stream);
+}
+
+int nrt_map_volumes(const NrtPlan* plan, const NrtParams* params, const int32_t* dims, float* vol_uncert, float* vol_sdf, void* stream) {
+  NRT_REQUIRE(plan && dims && vol_uncert && vol_sdf && dims[0] > 0 && dims[1] > 0 && dims[2] > 0, "map_volumes arguments");
+  if (int rc = check_params(params)) return rc;
+  return launch_map_volumes(plan, params, dims, vol_uncert, vol_sdf, (cudaStream_t)stream);
 }
 
 /* ---- device-resident ray sampling ---- */

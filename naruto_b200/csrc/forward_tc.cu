@@ -105,13 +105,22 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
 }
 
 // ---------------------------------------------------------------------------------------------
-// point decode
+// point decode.  Points come from an array x[n,3] (already normalised to the bound) or, when x == NULL, from the regular
+// lattice of get_map_volumes (src/slam/coslam/coslam_utils.py:58-97): torch.linspace per axis, meshgrid 'ij', normalised.
 // ---------------------------------------------------------------------------------------------
+struct LatticeSrc {
+  int n[3];           // lattice points per axis
+  float lo[3], hi[3]; // float32 bound
+  float step[3];      // float32((hi - lo) / (n - 1)), the linspace step
+  float* vol_uncert;  // [n0,n1,n2]: softplus(uncert) + 0.01 where 0 <= sdf < 0.5, else 0
+  float* vol_sdf;     // [n0,n1,n2]
+};
+
 template <bool COLOR>
 __global__ void __launch_bounds__(TC_THREADS, 2) points_fwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
                                                                       const float* __restrict__ x, int64_t n,
                                                                       float* __restrict__ raw, float* __restrict__ sdf_uncert,
-                                                                      float* __restrict__ geo) {
+                                                                      float* __restrict__ geo, const LatticeSrc lat) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* rest;
   TileCtx c = cta_prologue<TC_COLS>(smem_raw, prm, &rest);
@@ -124,12 +133,26 @@ __global__ void __launch_bounds__(TC_THREADS, 2) points_fwd_tc_kernel(const __gr
     const bool active = pt < n;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     if (active) {
-      x0 = __ldg(x + pt * 3);
-      x1 = __ldg(x + pt * 3 + 1);
-      x2 = __ldg(x + pt * 3 + 2);
+      if (x) {
+        x0 = __ldg(x + pt * 3);
+        x1 = __ldg(x + pt * 3 + 1);
+        x2 = __ldg(x + pt * 3 + 2);
+      } else {
+        const int k2 = (int)(pt % lat.n[2]), k1 = (int)((pt / lat.n[2]) % lat.n[1]), k0 = (int)(pt / ((int64_t)lat.n[2] * lat.n[1]));
+        x0 = normalise1(P, 0, linspace_at(lat.lo[0], lat.hi[0], lat.step[0], lat.n[0], k0));
+        x1 = normalise1(P, 1, linspace_at(lat.lo[1], lat.hi[1], lat.step[1], lat.n[1], k1));
+        x2 = normalise1(P, 2, linspace_at(lat.lo[2], lat.hi[2], lat.step[2], lat.n[2], k2));
+      }
     }
     PointOut o;
     decode_tile<COLOR>(P, c, grid, prm.uncert, active, x0, x1, x2, nullptr, o);
+    if (active && lat.vol_sdf && half == 0) {
+      // get_map_volumes: uncertainty only where the point is just outside the surface
+      const float sdf = o.o8[0];
+      const float u = softplusf_(uncert_sample(P, prm.uncert, x0, x1, x2)) + 0.01f;
+      lat.vol_sdf[pt] = sdf;
+      lat.vol_uncert[pt] = (sdf >= 0.0f && sdf < 0.5f) ? u : 0.0f;
+    }
     if (active) {
       if (half == 0) {
         if (raw) {
@@ -275,10 +298,36 @@ int launch_decode_fwd(const NrtPlan* plan, const NrtParams* prm, const float* x,
   }
   const int64_t tiles = (n + 127) / 128;
   const int blocks = (int)(tiles < 2 * plan->sm_count ? tiles : 2 * plan->sm_count);
+  LatticeSrc none{};
   if (with_color)
-    points_fwd_tc_kernel<true><<<blocks, TC_THREADS, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
+    points_fwd_tc_kernel<true><<<blocks, TC_THREADS, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo, none);
   else
-    points_fwd_tc_kernel<false><<<blocks, TC_THREADS, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo);
+    points_fwd_tc_kernel<false><<<blocks, TC_THREADS, kPointsSmem, st>>>(plan->dev, *prm, x, n, raw, sdf_uncert, geo, none);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
+
+// dense uncertainty + SDF sweep over the lattice of get_map_volumes; dims = lattice points per axis
+int launch_map_volumes(const NrtPlan* plan, const NrtParams* prm, const int* dims, float* vol_uncert, float* vol_sdf,
+                       cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    NRT_CUDA_CHECK(cudaFuncSetAttribute(points_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPointsSmem));
+    attr_set = true;
+  }
+  LatticeSrc lat{};
+  for (int a = 0; a < 3; ++a) {
+    lat.n[a] = dims[a];
+    lat.lo[a] = plan->cfg.bound_min[a];
+    lat.hi[a] = plan->cfg.bound_max[a];
+    lat.step[a] = dims[a] > 1 ? (lat.hi[a] - lat.lo[a]) / (float)(dims[a] - 1) : 0.f;
+  }
+  lat.vol_uncert = vol_uncert;
+  lat.vol_sdf = vol_sdf;
+  const int64_t n = (int64_t)dims[0] * dims[1] * dims[2];
+  const int64_t tiles = (n + 127) / 128;
+  const int blocks = (int)(tiles < 2 * plan->sm_count ? tiles : 2 * plan->sm_count);
+  points_fwd_tc_kernel<false><<<blocks, TC_THREADS, kPointsSmem, st>>>(plan->dev, *prm, nullptr, n, nullptr, nullptr, nullptr, lat);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

@@ -172,6 +172,17 @@ class FieldPlan:
         cp, cg = P.c_params(), G.c_grads()
         L.check(self.lib.nrt_decode_bwd(self.h, C.byref(cp), L.ptr(x), n, L.ptr(draw), C.byref(cg), L.ptr(ws), _stream()))
 
+    def map_volumes(self, P: FieldTensors, voxel_size: float):
+        """get_map_volumes (src/slam/coslam/coslam_utils.py:58-97) on the device -> (uncert_vol, sdf_vol) device tensors."""
+        b = self.bound
+        dims = [round(float(b[i, 1] - b[i, 0]) / voxel_size + 0.0005) + 1 for i in range(3)]     # getVoxels, tp/utils.py:36-43
+        dev = P.grid.device
+        unc = torch.empty(dims, dtype=torch.float32, device=dev)
+        sdf = torch.empty(dims, dtype=torch.float32, device=dev)
+        cp = P.c_params()
+        L.check(self.lib.nrt_map_volumes(self.h, C.byref(cp), (C.c_int32 * 3)(*dims), L.ptr(unc), L.ptr(sdf), _stream()))
+        return unc, sdf
+
     # ---- rays ----------------------------------------------------------------------------------
     def sample_z(self, target_d, u=None, perturb=None, seed=0):
         td = _f32c(target_d).reshape(-1)

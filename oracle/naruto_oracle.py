@@ -385,6 +385,23 @@ def total_loss(ret, spec, smooth=None):
 # ------------------------------------------------------------------------------------------------
 # L2: camera rays and one whole mapping iteration (optimiser included)
 # ------------------------------------------------------------------------------------------------
+def map_volumes(P, spec, voxel_size):
+    """get_map_volumes (src/slam/coslam/coslam_utils.py:58-97) with getVoxels (tp/utils.py:26-50): lattice by torch.linspace
+    per axis, normalise, query_sdf(return_uncert=True), uncert = softplus + 0.01 kept only where 0 <= sdf < 0.5.
+    (The reference also evaluates and discards an `embed` pass)  -> (uncert_vol, sdf_vol)"""
+    bb = torch.tensor(spec.bound, dtype=torch.float32)
+    lo, hi = [float(v) for v in bb[:, 0]], [float(v) for v in bb[:, 1]]
+    n = [round((hi[i] - lo[i]) / voxel_size + 0.0005) for i in range(3)]
+    tx, ty, tz = (torch.linspace(lo[i], hi[i], n[i] + 1) for i in range(3))
+    pts = torch.stack(torch.meshgrid(tx, ty, tz, indexing='ij'), -1).to(torch.float32)
+    x = (pts - bb[:, 0]) / (bb[:, 1] - bb[:, 0])
+    su = query_sdf(x, P, spec, return_uncert=True)
+    sdf, uncert = su[..., 0], su[..., 1]
+    um = F.softplus(uncert) + 0.01
+    um = torch.where((sdf >= 0) & (sdf < 0.5), um, torch.zeros_like(um))
+    return um, sdf
+
+
 def camera_rays(H, W, fx, fy, cx, cy):
     """get_camera_rays (tp/datasets/utils.py:24-57), OpenGL convention, un-normalised."""
     i, j = torch.meshgrid(torch.arange(W, dtype=torch.float32), torch.arange(H, dtype=torch.float32), indexing='xy')

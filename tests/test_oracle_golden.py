@@ -104,3 +104,16 @@ def test_train_losses_and_grads_match_reference(spec, tag):
     np.testing.assert_allclose(gg[idx].numpy(), g['grid_grad_probe'], rtol=1e-4, atol=1e-6 * np.abs(g['grid_grad_probe']).max())
     assert abs(gg.double().norm().item() - float(g['grid_grad_l2'])) <= 1e-5 * float(g['grid_grad_l2'])
     assert int((gg != 0).sum()) == int(g['grid_grad_nnz'])
+
+
+@pytest.mark.parametrize('tag', ['a', 'b'])
+def test_map_volumes_match_reference(spec, tag):
+    """oracle.map_volumes vs the reference's own get_map_volumes + query_sdf (oracle/make_golden_volumes.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'map_volumes_small.npz'))
+    P = no.init_params(spec, seed=int(g[f'seed_{tag}']), grid_range=float(g[f'range_{tag}']), uncert_jitter=1.0)
+    um, sdf = no.map_volumes(P, spec, 0.25)
+    assert tuple(sdf.shape) == g[f'sdf_{tag}'].shape == (20, 23, 15)
+    assert np.abs(sdf.numpy() - g[f'sdf_{tag}']).max() <= 1e-6 * max(1.0, np.abs(g[f'sdf_{tag}']).max())
+    assert np.abs(um.numpy() - g[f'uncert_{tag}']).max() <= 1e-5
+    assert (g[f'uncert_{tag}'] > 0).any() and (g[f'uncert_{tag}'] == 0).any()       # both sides of the surface mask
