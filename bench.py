@@ -117,6 +117,29 @@ def cpu_reference(n_rays, steps, warmup, seed=0):
     return sum(times), torch.get_num_threads()
 
 
+def torch_gpu_reference(n_rays, dev, torch, iters=8):
+    from oracle import naruto_oracle as no
+    from naruto_b200.synthetic import SyntheticFrame
+    spec = no.office0_spec(n_samples_d=N_SAMPLES_D)
+    P = no.init_params(spec, seed=0).to(dev).clone(requires_grad=True)
+    opt = no.MappingOptimisers(P)
+    frame = SyntheticFrame(spec.bound, seed=0)
+    ts = []
+    for it in range(iters):
+        o, d, rgb, td = [t.to(dev) for t in frame.sample(n_rays)]
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        u = torch.rand(n_rays, spec.n_samples, device=dev)
+        no.mapping_iteration(P, opt, o, d, rgb, td, spec, it, u=u,
+                             smooth_draws=(torch.rand(3, device=dev), torch.rand(1, 1, 1, 3, device=dev)))
+        b.record()
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    t = statistics.median(ts[3:])
+    return {'value': n_rays / t * 1e3, 'unit': UNIT, 'ms_per_step': round(t, 3),
+            'what': f'oracle/naruto_oracle.py mapping_iteration with torch CUDA ops on the same GPU, {n_rays} rays x {S} samples, fp32'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -322,6 +345,14 @@ def run_ours(args):
                  'ms': round(t_sw, 3), 'rays_per_s': n_sw / t_sw * 1e3, 'algorithmic_GB_per_s': round(gbs, 1),
                  'frac_of_hbm_peak': round(gbs / hbm_sw, 4), 'finite': bool(torch.isfinite(sw_out.depth).all().item())}
         del sw_out, o, d, td
+    gpu_torch = None
+    if rank == 0 and world == 1 and args.torch_gpu_baseline:
+        # the reference's Python path restated in torch ops (the oracle), run on THIS GPU -- the
+        # "reference PyTorch-GPU path" denominator of the north_star's >= 10x target.  ~150 ATen launches per iteration.
+        try:
+            gpu_torch = torch_gpu_reference(B, dev, torch)
+        except Exception as e:          # e.g. out of memory: report, never fail the bench
+            gpu_torch = {'error': repr(e)[:200]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu, k_cpu = 1024, 5
         tot, threads = cpu_reference(n_cpu, k_cpu, 1)
@@ -351,6 +382,8 @@ def run_ours(args):
     }
     if sweep is not None:
         line['sweep'] = sweep
+    if gpu_torch is not None:
+        line['torch_gpu_baseline'] = gpu_torch
     if cpu is not None:
         line['cpu_baseline'] = cpu
     print(json.dumps(line))
@@ -368,6 +401,8 @@ def main():
     ap.add_argument('--ref-rays', type=int, default=1024, help='rays per step for --impl reference')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sweep-rays', type=int, default=1 << 20, help='rays of the forward-only sweep (0 = skip)')
+    ap.add_argument('--torch-gpu-baseline', action='store_true',
+                    help='also time the oracle (reference Python path restated in torch ops) on the GPU')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
