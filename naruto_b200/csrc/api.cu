@@ -92,6 +92,11 @@ int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
     d.lv[l].res2 = res * res;
     d.lv[l].magic = (uint32_t)((1ull << 32) / size);
     d.lv[l].agg = res <= 32u ? 3u : res <= 64u ? 2u : 0u;
+    {
+      const uint64_t span = 1ull + res + (uint64_t)res * res;
+      d.lv[l].lim = size > span ? (uint32_t)(size - span) : 0u;
+      d.lv[l].pad_ = 0u;
+    }
     offset += size;
   }
   NRT_REQUIRE(offset < (1ull << 31), "hash table too large for 32-bit entry offsets");

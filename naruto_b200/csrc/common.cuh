@@ -29,6 +29,9 @@ struct DevLevel {
   uint32_t res2;      // res*res (mod 2^32)
   uint32_t magic;     // floor(2^32 / size): umulhi(v, magic) is floor(v/size) or one less, for any 32-bit v
   uint32_t agg;       // > 0: cells are coarse relative to the sample spacing: merge runs of up to 2^agg samples before the gradient RED
+  uint32_t lim;       // dense levels: size - (1 + res + res2) (0 if that is negative): a cell whose base index is below lim has all
+                      // eight corners inside [0, size) without uint32 wrap-around, so the % size is the identity
+  uint32_t pad_;
 };
 
 struct DevPlan {
@@ -172,23 +175,118 @@ __device__ __forceinline__ LevelPos level_corners(const DevLevel& L, float x0, f
   return p;
 }
 
-// gathers one level: returns the two interpolated features
+// The four (y, z) corner entries of one level at x-corner xc (0 / 1), relative to the level's first entry, and the cell
+// fractions.  Same arithmetic as level_corners().
+__device__ __forceinline__ void level_offsets_x(const DevLevel& L, uint32_t xc, float x0, float x1, float x2,
+                                                uint32_t* __restrict__ idx, float* __restrict__ fr) {
+  const LevelPos p = level_pos(L, x0, x1, x2);
+  fr[0] = p.f[0];
+  fr[1] = p.f[1];
+  fr[2] = p.f[2];
+  const uint32_t gx = p.g[0] + xc;
+  if (L.hashed) {
+    const uint32_t hy0 = p.g[1] * 2654435761u, hz0 = p.g[2] * 805459861u;
+    const uint32_t hy[2] = {hy0, hy0 + 2654435761u}, hz[2] = {hz0, hz0 + 805459861u};
+    const uint32_t m = L.size - 1u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) idx[k] = (gx ^ hy[k & 1] ^ hz[k >> 1]) & m;
+  } else {
+    const uint32_t base = p.g[0] + p.g[1] * L.res + p.g[2] * L.res2;
+    if (base < L.lim) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) idx[k] = base + xc + (k & 1) * L.res + (k >> 1) * L.res2;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) idx[k] = mod_size(L, base + xc + (k & 1) * L.res + (k >> 1) * L.res2);
+    }
+  }
+}
+
+// Pair-cooperative gather of NL consecutive levels.  The lanes (2i, 2i+1) of a warp serve their two points together: for
+// each point the even lane reads the four x-corner-0 entries and the odd lane the four x-corner-1 entries of every level,
+// so one load instruction carries 16 points x 2 x-neighbours.  x-neighbours are adjacent in dense levels and differ only in
+// the low index bits under tcnn's coherent hash (prime 1 on x), i.e. they share a 32-byte sector three times out of four and
+// a 128-byte line 15 times out of 16: the L1 tag look-ups and wavefronts per gathered byte -- the resource that bounds this
+// kernel -- drop by ~45% against one-point-per-lane.  Each lane weights what it read (it knows both points), and one shuffle
+// per feature folds the two x-halves.  Summation order: x-corner halves first (y, z order inside), then their sum.
+template <int NL>
+__device__ __forceinline__ void gather_levels_paired(const DevLevel* __restrict__ lv, const float2* __restrict__ grid, float x0,
+                                                     float x1, float x2, float* __restrict__ f) {
+  const bool odd = threadIdx.x & 1;
+  const float y0 = __shfl_xor_sync(0xffffffffu, x0, 1), y1 = __shfl_xor_sync(0xffffffffu, x1, 1),
+              y2 = __shfl_xor_sync(0xffffffffu, x2, 1);
+  // point A belongs to the even lane of the pair, point B to the odd lane
+  const float a0 = odd ? y0 : x0, a1 = odd ? y1 : x1, a2 = odd ? y2 : x2;
+  const float b0 = odd ? x0 : y0, b1 = odd ? x1 : y1, b2 = odd ? x2 : y2;
+  const uint32_t xc = odd ? 1u : 0u;
+  uint32_t idx[NL][8];
+  float fr[NL][6];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    level_offsets_x(lv[l], xc, a0, a1, a2, idx[l], fr[l]);
+    level_offsets_x(lv[l], xc, b0, b1, b2, idx[l] + 4, fr[l] + 3);
+  }
+  float2 v[NL][8];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    const float2* base = grid + lv[l].offset;
+    asm("" : "+l"(base));      // keep the level's base pointer whole: each address is then one 32x32+64 multiply-add
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[l][c] = ldg_f2(base + idx[l][c]);
+  }
+#pragma unroll
+  for (int l = 0; l < NL; ++l) {
+    float part[2][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {          // q = 0: point A, 1: point B
+      const float fx = fr[l][3 * q], fy = fr[l][3 * q + 1], fz = fr[l][3 * q + 2];
+      const float wx = odd ? fx : 1.0f - fx;
+      const float wy[2] = {1.0f - fy, fy}, wz[2] = {1.0f - fz, fz};
+      float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = (wx * wy[k & 1]) * wz[k >> 1];
+        r0 = fmaf(w, v[l][4 * q + k].x, r0);
+        r1 = fmaf(w, v[l][4 * q + k].y, r1);
+      }
+      part[q][0] = r0;
+      part[q][1] = r1;
+    }
+    // the even lane keeps point A and needs the odd lane's half of it; the odd lane keeps B
+    const float s0 = odd ? part[0][0] : part[1][0], s1 = odd ? part[0][1] : part[1][1];
+    const float g0 = __shfl_xor_sync(0xffffffffu, s0, 1), g1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    const float k0 = odd ? part[1][0] : part[0][0], k1 = odd ? part[1][1] : part[0][1];
+    f[2 * l] = odd ? g0 + k0 : k0 + g0;        // x-corner-0 half first, on both lanes
+    f[2 * l + 1] = odd ? g1 + k1 : k1 + g1;
+  }
+}
+
+// gathers one level: returns the two interpolated features.  Summation order as gather_levels_paired(): the four (y, z)
+// corners of each x-corner half, then the sum of the two halves -- every kernel of the library produces the same bits.
 __device__ __forceinline__ float2 level_gather(const DevLevel& L, const float2* __restrict__ grid, float x0, float x1,
                                                float x2) {
   uint32_t idx[8];
-  float w[8];
-  level_corners(L, x0, x1, x2, idx, w);
+  float w_unused[8];
+  const LevelPos p = level_corners(L, x0, x1, x2, idx, w_unused);
   const float2* base = grid + L.offset;
   float2 v[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) v[c] = ldg_f2(base + idx[c]);
-  float2 r = make_float2(0.f, 0.f);
+  const float wy[2] = {1.0f - p.f[1], p.f[1]}, wz[2] = {1.0f - p.f[2], p.f[2]};
+  float2 h[2];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    r.x = fmaf(w[c], v[c].x, r.x);
-    r.y = fmaf(w[c], v[c].y, r.y);
+  for (int xc = 0; xc < 2; ++xc) {
+    const float wx = xc ? p.f[0] : 1.0f - p.f[0];
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float w = (wx * wy[k & 1]) * wz[k >> 1];
+      r0 = fmaf(w, v[xc + 2 * k].x, r0);
+      r1 = fmaf(w, v[xc + 2 * k].y, r1);
+    }
+    h[xc] = make_float2(r0, r1);
   }
-  return r;
+  return make_float2(h[0].x + h[1].x, h[0].y + h[1].y);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -269,28 +367,46 @@ __device__ __forceinline__ void oneblob16(float x, float* __restrict__ bins) {
 
 // Same encoding, evaluated sparsely.  With boundary values B_b = wrapped_cdf(b/16 - x) (b = 0..15) and B_16 = B_0 + 1,
 // bins[b] = B_{b+1} - B_b.  For x in [0, 1) and i0 = floor(16 x), the quartic kernel (support |u| < 1, clamped outside)
-// makes every boundary except b = i0, i0 + 1 and the wrap-around boundary b = 0 saturate: B_b = 0 + 0 + 1 for b < i0 and
-// 1 + 0 + 1 for b > i0 + 1.  The three live boundaries are evaluated with the dense formula, so the result equals
-// oneblob16() bit for bit except when x sits within one ulp of a bin boundary (difference <= 6e-8).  x outside [0, 1)
-// (sample points outside the bound) takes the dense path.
+// makes every boundary except b = i0 and i0 + 1 (and, through the wrap-around, b = 0 / 16 when i0 is 0 or 15) saturate to
+// exactly 0 + 0 + 1 (b < i0) or 1 + 0 + 1 (b > i0 + 1).  Of wrapped_cdf's three terms only the centre one is live at the two
+// live boundaries (the -1 image is exactly 0, the +1 image exactly 1), so
+//     B_i0 = qa + 1,  B_{i0+1} = qb + 1,      qa = quartic_cdf(i0/16 - x),  qb = quartic_cdf((i0+1)/16 - x)
+// and only three bins are non-zero, at (i0 - 1) mod 16, i0, (i0 + 1) mod 16:
+//     ca - 1 | cb - ca | 2 - cb          (i0 = 0:  first = (ca + 1) - 2 in bin 15;   i0 = 15:  last = 1 - qb in bin 0)
+// -- the same expressions, in the same order, as oneblob16() evaluates for those bins, so the result equals it bit for bit
+// except when x sits within an ulp of a bin boundary (difference <= 6e-8).  The three values are then rotated into place
+// with a 4-stage barrel rotation whose known-zero lanes fold away at compile time (36 selects instead of a 16 x 3 compare
+// chain).  x outside [0, 1) (sample points outside the bound) takes the dense path.
 __device__ __forceinline__ void oneblob16_fast(float x, float* __restrict__ bins) {
   if (!(x >= 0.0f && x < 1.0f)) {
     oneblob16(x, bins);
     return;
   }
   const int i0 = min((int)(x * (float)NRT_BINS), NRT_BINS - 1);
-  const float c0 = wrapped_cdf(0.0f - x);
-  const float ca = wrapped_cdf((float)i0 * (1.0f / NRT_BINS) - x);
-  const float cb = wrapped_cdf((float)(i0 + 1) * (1.0f / NRT_BINS) - x);
-  const float c16 = c0 + 1.0f;
-  float left = c0;
+  const float qa = quartic_cdf((float)i0 * (1.0f / NRT_BINS) - x);
+  const float qb = quartic_cdf((float)(i0 + 1) * (1.0f / NRT_BINS) - x);
+  const float ca = qa + 1.0f, cb = qb + 1.0f;
+  const float va = i0 == 0 ? (ca + 1.0f) - 2.0f : ca - 1.0f;
+  const float vb = cb - ca;
+  const float vc = i0 == NRT_BINS - 1 ? 1.0f - qb : 2.0f - cb;
+  // rotate [va, vb, vc, 0, ...] right by r = (i0 - 1) mod 16
+  const int r = (i0 + NRT_BINS - 1) & (NRT_BINS - 1);
+  float a[NRT_BINS], b[NRT_BINS];
 #pragma unroll
-  for (int b = 0; b < NRT_BINS; ++b) {
-    const int r = b + 1;
-    const float right = r == NRT_BINS ? c16 : r < i0 ? 1.0f : r == i0 ? ca : r == i0 + 1 ? cb : 2.0f;
-    bins[b] = right - left;
-    left = right;
+  for (int k = 0; k < NRT_BINS; ++k) a[k] = 0.f;
+  a[0] = va;
+  a[1] = vb;
+  a[2] = vc;
+#pragma unroll
+  for (int sft = 0; sft < 4; ++sft) {
+    const bool on = (r >> sft) & 1;
+#pragma unroll
+    for (int k = 0; k < NRT_BINS; ++k) b[k] = on ? a[(k - (1 << sft)) & (NRT_BINS - 1)] : a[k];
+#pragma unroll
+    for (int k = 0; k < NRT_BINS; ++k) a[k] = b[k];
   }
+#pragma unroll
+  for (int k = 0; k < NRT_BINS; ++k) bins[k] = a[k];
 }
 
 // normalisation to the bound (tp/model/scene_rep.py:172-173): two roundings, like the tensor ops

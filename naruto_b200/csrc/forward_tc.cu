@@ -20,6 +20,8 @@
 // Reference semantics: tp/model/scene_rep.py:160-178 (run_network), src/slam/coslam/model/scene_rep.py:58-64,98-148
 // (calc_embedding / query_sdf / query_color_sdf), src/slam/coslam/model/decoder.py:29-41,99-116, and for the ray kernel
 // src/slam/coslam/model/scene_rep.py:150-225,66-96 with tp/model/scene_rep.py:64-84.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mlp_tc.cuh"
 
@@ -36,33 +38,21 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
                                             float* __restrict__ feat_out, PointOut& out) {
   const int half = tc_half();
   // ---- encodings -> TMEM ----
-  // four hash levels per iteration (32 independent 8-byte gathers in flight per thread); rolled loops keep the tile body
-  // inside the instruction cache
+  // two hash levels per iteration, gathered pair-cooperatively (common.cuh: gather_levels_paired); rolled loops keep the
+  // tile body inside the instruction cache.  Inactive rows sit at x = 0: finite values, results dropped.
 #pragma unroll 1
-  for (int gi = 0; gi < 2; ++gi) {
-    const int g = 2 * gi + half;
-    float f[8];
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      float2 v = make_float2(0.f, 0.f);
-      if (active) v = level_gather(P.lv[g * 4 + l], grid, x0, x1, x2);
-      f[2 * l] = v.x;
-      f[2 * l + 1] = v.y;
-    }
-    if (feat_out) {
-      reinterpret_cast<float4*>(feat_out)[g * 2] = make_float4(f[0], f[1], f[2], f[3]);
-      reinterpret_cast<float4*>(feat_out)[g * 2 + 1] = make_float4(f[4], f[5], f[6], f[7]);
-    }
-    stage8(c, TA_X0 + 8 * g, f);
+  for (int gi = 0; gi < 4; ++gi) {
+    const int g = 2 * (gi >> 1) + half;         // this half's groups of four levels: {half, half + 2}
+    const int l0 = 4 * g + 2 * (gi & 1);
+    float f[4];
+    gather_levels_paired<2>(P.lv + l0, grid, x0, x1, x2, f);
+    if (feat_out) reinterpret_cast<float4*>(feat_out)[l0 >> 1] = make_float4(f[0], f[1], f[2], f[3]);
+    stage4(c, TA_X0 + 2 * l0, f);
   }
 #pragma unroll 1
   for (int d = 2 * half; d < 2 + half; ++d) {
     float bins[NRT_BINS];
     oneblob16_fast(d == 0 ? x0 : d == 1 ? x1 : x2, bins);
-    if (!active) {
-#pragma unroll
-      for (int b = 0; b < NRT_BINS; ++b) bins[b] = 0.f;
-    }
     stage16(c, TA_OB + 16 * d, bins);
   }
   out.unc = (half == 1 && active) ? uncert_sample(P, ug, x0, x1, x2) : 0.f;
@@ -332,10 +322,21 @@ int launch_map_volumes(const NrtPlan* plan, const NrtParams* prm, const int* dim
   return NRT_OK;
 }
 
+int launch_render_fwd_ws(const NrtPlan*, const NrtParams*, const float*, const float*, const float*, int64_t, const float*,
+                         const float*, int, uint64_t, const NrtRenderOut*, cudaStream_t);   // forward_ws.cu
+
 int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d,
                       const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
                       const NrtRenderOut* out, cudaStream_t st) {
   if (n_rays == 0) return NRT_OK;
+  // The warp-specialised kernel (forward_ws.cu) is the product path; NRT_RENDER_IMPL=tc selects the one-role kernel below
+  // (same arithmetic, bit-identical results) for A/B measurements.
+  static int use_ws = -1;
+  if (use_ws < 0) {
+    const char* e = getenv("NRT_RENDER_IMPL");
+    use_ws = (e && e[0] == 't' && e[1] == 'c' && e[2] == 0) ? 0 : 1;
+  }
+  if (use_ws) return launch_render_fwd_ws(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, st);
   const int S = plan->dev.S;
   const int slots = 2 * plan->sm_count;
   // rays per block: as many blocks as there are CTA slots (one balanced wave), capped by the staging buffer

@@ -149,7 +149,20 @@ __device__ __forceinline__ void stage8(const TileCtx& c, int col, const float* v
   tmem_st8(c.lane_tb + TC_ALO + col, lo);
 }
 
-__device__ __forceinline__ int tc_half() { return (int)(threadIdx.x >> 7); }      // which half of the columns this thread owns
+// which half of the columns this thread owns; read through a lane-0 broadcast so the compiler knows it is warp-uniform
+// (branches on it become uniform branches, level constants indexed by it live in uniform registers)
+__device__ __forceinline__ void stage4(const TileCtx& c, int col, const float* v) {
+  float hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = tf32_hi(v[i]);
+    lo[i] = v[i] - hi[i];
+  }
+  tmem_st4(c.lane_tb + TC_AHI + col, hi);
+  tmem_st4(c.lane_tb + TC_ALO + col, lo);
+}
+
+__device__ __forceinline__ int tc_half() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0); }
 __device__ __forceinline__ int tc_row() { return (int)(threadIdx.x & 127); }      // point / TMEM lane of this thread
 
 // common prologue: forward weights -> smem, barrier init, TMEM allocation.
