@@ -183,7 +183,7 @@ def time_kernels(plan, ms, torch, flush, reps=10):
             ts.append(a.elapsed_time(b))
         return statistics.median(ts)
 
-    res['render_fwd_tc_kernel'] = (timed(lambda: plan.render_fwd(ms.P, ms.rays_o, ms.rays_d, ms.target_d, ms.out, u=ms.u)),
+    res['render_fwd_ws_kernel'] = (timed(lambda: plan.render_fwd(ms.P, ms.rays_o, ms.rays_d, ms.target_d, ms.out, u=ms.u)),
                                    B * BYTES_PER_RAY_FWD)
     plan.loss_partial(ms.out, ms.target_rgb, ms.target_d, ms.stats)
     plan.loss_finalize(ms.stats, ms.losses)
@@ -312,14 +312,14 @@ def run_ours(args):
         if os.path.exists(tj):
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (same workload)
             tr = json.load(open(tj))['dram_bytes_per_launch']
-            traffic = tr.get('decode_bwd_tc_kernel' if 'bwd' in top else 'render_fwd_tc_kernel')
+            traffic = tr.get('decode_bwd_tc_kernel' if 'bwd' in top else 'render_fwd_ws_kernel')
         roof = {'bound': 'hbm', 'kernel': top, 'achieved': round(ach, 1), 'peak': hbm, 'unit': 'GB/s', 'frac': round(ach / hbm, 4),
                 'traffic': traffic, 'peak_source': how,
                 'note': 'algorithmic bytes (SURVEY 8d) / CUDA-event time of the kernel launched alone, L2 flushed; at hash_size 16 '
                         'the 6.5 MB table is L2-resident so the gather fraction is an accounting convention; the backward entry '
                         'is the launch pair composite_bwd_kernel (7% of it) + decode_bwd_tc_kernel, traffic is the latter\'s',
-                'hash_gather': {'kernel': 'render_fwd_tc_kernel', 'achieved': kern['render_fwd_tc_kernel']['algorithmic_GB_per_s'],
-                                'frac': round(kern['render_fwd_tc_kernel']['algorithmic_GB_per_s'] / hbm, 4)}}
+                'hash_gather': {'kernel': 'render_fwd_ws_kernel', 'achieved': kern['render_fwd_ws_kernel']['algorithmic_GB_per_s'],
+                                'frac': round(kern['render_fwd_ws_kernel']['algorithmic_GB_per_s'] / hbm, 4)}}
     sweep = None
     if rank == 0 and world == 1 and args.sweep_rays > 0:
         # BASELINE.json configs[4]: uncertainty-only forward sweep, 1M rays x 128 samples, no backward, only the per-ray

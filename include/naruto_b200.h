@@ -174,6 +174,15 @@ int nrt_render_fwd(const NrtPlan* plan, const NrtParams* params, const float* ra
                    const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb,
                    uint64_t seed, const NrtRenderOut* out, void* stream);
 
+/* nrt_render_fwd followed by nrt_loss_partial in ONE launch (the training path: JointEncodingNaruto.forward,
+ * src/slam/coslam/model/scene_rep.py:227-287 = render_rays + the loss sums of tp/model/utils.py:81-148): the
+ * compositing warps accumulate the shard's loss statistics while the ray's samples are still on chip.  `stats` is the
+ * buffer of nrt_loss_partial (nrt_loss_stats_bytes() bytes, zero-filled once at allocation) and receives the same
+ * NRT_N_STATS sums; out must provide rgb, depth, uncert, z_vals, raw (and feat for nrt_render_bwd). */
+int nrt_render_fwd_stats(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
+                         const float* target_rgb, const float* target_d, int64_t n_rays, const float* u, int perturb,
+                         uint64_t seed, const NrtRenderOut* out, double* stats, void* stream);
+
 /* raw2outputs + sdf2weights on caller-provided samples (JointEncodingNaruto.raw2outputs,
  * src/slam/coslam/model/scene_rep.py:66-96): raw dev [B,n_samples,5], z dev [B,n_samples]; fills the per-ray
  * fields and `weights` of out. */

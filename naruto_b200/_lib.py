@@ -60,6 +60,8 @@ SIGNATURES = {
     'nrt_composite_fwd': (C.c_int, [_P, c_fp, c_fp, C.c_int64, C.c_int32, C.POINTER(NrtRenderOut), _P]),
     'nrt_render_fwd': (C.c_int, [_P, C.POINTER(NrtParams), c_fp, c_fp, c_fp, C.c_int64, c_fp, c_fp, C.c_int, C.c_uint64,
                                  C.POINTER(NrtRenderOut), _P]),
+    'nrt_render_fwd_stats': (C.c_int, [_P, C.POINTER(NrtParams), c_fp, c_fp, c_fp, c_fp, C.c_int64, c_fp, C.c_int, C.c_uint64,
+                                       C.POINTER(NrtRenderOut), c_fp, _P]),
     'nrt_loss_stats_bytes': (C.c_int64, []),
     'nrt_loss_partial': (C.c_int, [_P, C.POINTER(NrtRenderOut), c_fp, c_fp, C.c_int64, c_fp, _P]),
     'nrt_loss_finalize': (C.c_int, [_P, c_fp, c_fp, _P]),

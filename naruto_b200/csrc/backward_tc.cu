@@ -158,6 +158,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
   }
   for (int i = t; i < 128; i += BWD_THREADS) w4s[i] = i < 96 ? __ldg(prm.w4 + i) : 0.f;
   for (int i = t; i < YT_FLOATS; i += BWD_THREADS) yt[i] = 0.f;   // rows 83.. and the slack stay zero for the whole kernel
+  // second mbarrier: completion of the weight-gradient GEMM, which nobody needs before the NEXT tile overwrites X^T / Y^T
+  uint64_t* bar_wg = reinterpret_cast<uint64_t*>(smem_raw + 16);
+  uint32_t ph_wg = 0u;
+  if (t == 0) {
+    mbar_init(bar_wg, 1);
+    fence_mbar_init();
+  }
   cta_prologue_finish(smem_raw, c);
   const uint32_t bw_hi = smem_u32(bw), bw_lo = smem_u32(bw + BW_FLOATS);
   const uint32_t xt_s = smem_u32(xt), yt_s = smem_u32(yt);
@@ -197,6 +204,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
         f[4 * q + 1] = v.y;
         f[4 * q + 2] = v.z;
         f[4 * q + 3] = v.w;
+      }
+      // the previous tile's weight-gradient GEMM still reads X^T / Y^T: wait for it here, with this tile's loads in flight
+      if (k > 0) {
+        __syncwarp();
+        mbar_wait(bar_wg, ph_wg);
+        ph_wg ^= 1u;
+        tc_fence_after();
       }
       float hi[16], lo[16];
 #pragma unroll
@@ -308,12 +322,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
       tc_fence_after();
       if (elect_one()) {
       issue_layer<32, 32>(c, TA_X0, bw_hi + BW_W1T * 4, bw_lo + BW_W1T * 4);
+      mma_commit(c.bar);                       // dfeat: waited for right below
       constexpr uint32_t idesc = idesc_tf32(128, 160, 0, 0);
       const uint64_t yd = smem_desc(yt_s, YT_ROWS * 16, 128), xd = smem_desc(xt_s, XT_ROWS * 16, 128);
 #pragma unroll
       for (int ks = 0; ks < 16; ++ks)
         mma_tf32_ss(c.tb + TC_DW, yd + (uint64_t)(2 * YT_ROWS * ks), xd + (uint64_t)(2 * XT_ROWS * ks), idesc, !(first_tile && ks == 0));
-      mma_commit(c.bar);
+      mma_commit(bar_wg);                      // weight gradients: waited for at the top of the next tile / before the flush
       }
     }
     first_tile = false;
@@ -352,6 +367,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
       }
     }
   }
+    if (!first_tile) {                          // the last tile's weight-gradient GEMM
+      __syncwarp();
+      mbar_wait(bar_wg, ph_wg);
+      tc_fence_after();
+    }
   }  // MLP threads
   // ---- flush the weight gradients: the thread pair of row r holds row r of D, half 0 columns 0..79, half 1 80..159 ----
   tc_fence_before();

@@ -34,6 +34,19 @@
 #define WS_BAR_EMPTY(g, s) (7 + 2 * (g) + (s))    // 128 MLP arrive + 256 gather sync
 #define WS_BAR_UNIT(g) (11 + (g))                 // all 384 threads of sub-CTA g
 
+// Optional fused loss statistics (what nrt_loss_partial computes from the materialised outputs; forward.cu:
+// loss_partial_kernel): the compositing warp already holds the ray's z / raw in shared memory and its integrals in
+// registers.  Per-warp fp64 partial sums live in shared memory, are folded per CTA at the end and reduced in CTA order by the
+// last CTA to finish, so the result does not depend on scheduling.
+struct LossFuse {
+  const float* target_rgb;   // NULL: statistics off
+  const float* target_d;
+  double* part;              // [gridDim.x][NRT_N_STATS]
+  unsigned int* counter;
+  double* stats;             // [NRT_N_STATS]
+};
+#define WS_STAT_SLOTS 12     // 11 sums + the minimum of uncert_map
+
 template <int K, int N>
 __device__ __forceinline__ void ws_run_layer(TileCtx& c, int g, bool issuer, int a_col, uint32_t wh, uint32_t wl) {
   tmem_st_wait();
@@ -69,7 +82,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
                                                                       const float* __restrict__ rays_d,
                                                                       const float* __restrict__ target_d, int64_t n_rays,
                                                                       const float* __restrict__ z_in, const float* __restrict__ u,
-                                                                      int perturb, uint64_t seed, int rpu, const NrtRenderOut out) {
+                                                                      int perturb, uint64_t seed, int rpu, const NrtRenderOut out,
+                                                                      const LossFuse lf) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // [2] MMA-complete mbarriers, one per MLP group
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
@@ -102,6 +116,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
   float* s_z = s_ray + rpu * 6;
   float* s_raw = s_z + rpu * S;
   const float2* grid = reinterpret_cast<const float2*>(prm.grid);
+  double* s_stat = reinterpret_cast<double*>(sw + 2 * FW_FLOATS + 2 * (WS_NST * WS_STAGE_FLOATS) + 2 * (rpu * (6 + 6 * S))) +
+                   warp * WS_STAT_SLOTS;                              // this warp's partial sums
+  if (lf.target_rgb && lane < WS_STAT_SLOTS) s_stat[lane] = lane == NRT_STAT_UNCERT_MIN ? 3.4e38 : 0.0;
 
   TileCtx c;
   c.tb = tmem_base + 256u * (uint32_t)g;
@@ -257,19 +274,98 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
         for (int s = lane; s < S; s += 32) out.z_vals[ray * S + s] = z[s];
       if (out.raw)
         for (int i = lane; i < S * 5; i += 32) out.raw[ray * S * 5 + i] = raw[i];
+      if (lf.target_rgb) {
+        // per-sample masks: front = z < d - tr ; back = z > d + tr ; sdf_mask = !front & !back & (d > 0)   (tp/model/utils.py:81-148)
+        const float td = __ldg(lf.target_d + ray);
+        const float tr = P.sc_trunc;
+        const float lo = __fsub_rn(td, tr), hi = __fadd_rn(td, tr);
+        float nfs = 0.f, fsq = 0.f, nsd = 0.f, ssq = 0.f;
+        for (int s = lane; s < S; s += 32) {
+          const float zz = z[s], sdf = raw[s * 5 + 3];
+          if (zz < lo) {
+            const float e = sdf - 1.0f;
+            nfs += 1.0f;
+            fsq = fmaf(e, e, fsq);
+          } else if (!(zz > hi) && td > 0.0f) {
+            const float e = __fadd_rn(zz, __fmul_rn(sdf, tr)) - td;
+            nsd += 1.0f;
+            ssq = fmaf(e, e, ssq);
+          }
+        }
+        nfs = warp_sum(nfs);
+        fsq = warp_sum(fsq);
+        nsd = warp_sum(nsd);
+        ssq = warp_sum(ssq);
+        if (lane == 0) {
+          const float e0 = ro.rgb[0] - __ldg(lf.target_rgb + ray * 3 + 0), e1 = ro.rgb[1] - __ldg(lf.target_rgb + ray * 3 + 1),
+                      e2 = ro.rgb[2] - __ldg(lf.target_rgb + ray * 3 + 2);
+          s_stat[NRT_STAT_N_RAYS] += 1.0;
+          s_stat[NRT_STAT_RGB_SQ] += (double)(e0 * e0) + (double)(e1 * e1) + (double)(e2 * e2);
+          s_stat[NRT_STAT_UNCERT_MIN] = fmin(s_stat[NRT_STAT_UNCERT_MIN], (double)ro.uncert);
+          if (td > 0.0f && td < P.depth_trunc) {
+            const float e = ro.depth - td;
+            s_stat[NRT_STAT_N_VALID] += 1.0;
+            s_stat[NRT_STAT_DEPTH_SQ] += (double)(e * e);
+            s_stat[NRT_STAT_INV2U] += (double)(1.0f / (2.0f * (ro.uncert + 1e-9f)));
+            s_stat[NRT_STAT_LOGU] += (double)logf(ro.uncert + 1e-9f);
+          }
+          s_stat[NRT_STAT_N_SAMPLES] += (double)S;
+          s_stat[NRT_STAT_N_FS] += (double)nfs;
+          s_stat[NRT_STAT_FS_SQ] += (double)fsq;
+          s_stat[NRT_STAT_N_SDF] += (double)nsd;
+          s_stat[NRT_STAT_SDF_SQ] += (double)ssq;
+        }
+      }
     }
     bar_sync(WS_BAR_UNIT(g), WS_SUB);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<WS_COLS>(tmem_base);
+  if (lf.target_rgb) {
+    // fold the 24 warps in warp order, publish this CTA's partial, let the last CTA reduce all partials in CTA order
+    volatile uint32_t* s_last = reinterpret_cast<volatile uint32_t*>(smem_raw + 32);    // header slack
+    const double* all = s_stat - warp * WS_STAT_SLOTS;
+    if (threadIdx.x < NRT_N_STATS) {
+      double v = 0.0;
+      if (threadIdx.x < NRT_N_STATS_SUM) {
+        for (int w = 0; w < WS_THREADS / 32; ++w) v += all[w * WS_STAT_SLOTS + threadIdx.x];
+      } else if (threadIdx.x == NRT_STAT_UNCERT_MIN) {
+        v = 3.4e38;
+        for (int w = 0; w < WS_THREADS / 32; ++w) v = fmin(v, all[w * WS_STAT_SLOTS + threadIdx.x]);
+      }
+      lf.part[(int64_t)blockIdx.x * NRT_N_STATS + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *s_last = atomicAdd(lf.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (*s_last && threadIdx.x < NRT_N_STATS) {
+      __threadfence();
+      double v = threadIdx.x == NRT_STAT_UNCERT_MIN ? 3.4e38 : 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) {
+        const double pv = lf.part[(int64_t)b * NRT_N_STATS + threadIdx.x];
+        v = threadIdx.x == NRT_STAT_UNCERT_MIN ? fmin(v, pv) : v + pv;
+      }
+      lf.stats[threadIdx.x] = v;
+      if (threadIdx.x == 0) *lf.counter = 0u;   // re-arm for the next launch
+    }
+  }
 }
 
 int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d,
                          const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
-                         const NrtRenderOut* out, cudaStream_t st) {
+                         const NrtRenderOut* out, const float* target_rgb, double* stats, cudaStream_t st) {
   if (n_rays == 0) return NRT_OK;
   const int S = plan->dev.S;
+  LossFuse lf{};
+  if (target_rgb) {          // stats buffer layout as launch_loss_partial (forward.cu): [stats(16) | counter | CTA partials]
+    lf.target_rgb = target_rgb;
+    lf.target_d = target_d;
+    lf.stats = stats;
+    lf.counter = reinterpret_cast<unsigned int*>(stats + NRT_N_STATS);
+    lf.part = stats + NRT_N_STATS + 2;
+  }
   const int64_t slots = 2 * (int64_t)plan->sm_count;
   // rays per block: every sub-CTA gets the same number of blocks (rounds), each block as large as the staging buffer allows
   const int cap = WS_UNIT_PTS / S > 1 ? WS_UNIT_PTS / S : 1;
@@ -278,7 +374,8 @@ int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float*
   if (rpu > cap) rpu = cap;
   if (rpu < 1) rpu = 1;
   const int64_t units = (n_rays + rpu - 1) / rpu;
-  const size_t smem = TC_SMEM_WEIGHTS + (size_t)(2 * WS_NST * WS_STAGE_FLOATS + 2 * rpu * (6 + 6 * S)) * sizeof(float);
+  const size_t smem = TC_SMEM_WEIGHTS + (size_t)(2 * WS_NST * WS_STAGE_FLOATS + 2 * rpu * (6 + 6 * S)) * sizeof(float) +
+                      (size_t)(WS_THREADS / 32) * WS_STAT_SLOTS * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
     NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -287,7 +384,7 @@ int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float*
   const int64_t want = (units + 1) / 2;
   const int blocks = (int)(want < plan->sm_count ? want : plan->sm_count);
   render_fwd_ws_kernel<<<blocks, WS_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed,
-                                                        (int)rpu, *out);
+                                                        (int)rpu, *out, lf);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

@@ -211,6 +211,18 @@ class FieldPlan:
                                         L.ptr(_f32c(u)) if u is not None else None, perturb, seed, C.byref(cs), _stream()))
         return out
 
+    def render_fwd_stats(self, P: FieldTensors, rays_o, rays_d, target_rgb, target_d, out: RenderBuffers, stats, u=None,
+                         perturb=None, seed=0):
+        """render_fwd + loss_partial in one launch (training path)."""
+        rays_o, rays_d = _f32c(rays_o), _f32c(rays_d)
+        perturb = self.perturb if perturb is None else int(perturb)
+        cp, cs = P.c_params(), out.c_struct()
+        L.check(self.lib.nrt_render_fwd_stats(self.h, C.byref(cp), L.ptr(rays_o), L.ptr(rays_d), L.ptr(_f32c(target_rgb)),
+                                              L.ptr(_f32c(target_d).reshape(-1)), rays_o.shape[0],
+                                              L.ptr(_f32c(u)) if u is not None else None, perturb, seed, C.byref(cs),
+                                              L.ptr(stats), _stream()))
+        return out
+
     def new_stats(self, device):
         return torch.zeros(self.lib.nrt_loss_stats_bytes() // 8, dtype=torch.float64, device=device)
 

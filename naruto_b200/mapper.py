@@ -83,8 +83,7 @@ class MappingStep:
             if self.smooth_on:
                 self.rand6.uniform_()                       # torch.rand(3), torch.rand((1,1,1,3))
         p.counter_add(self.map_step, 1); n += 1
-        p.render_fwd(self.P, self.rays_o, self.rays_d, self.target_d, self.out, u=self.u); n += 1
-        p.loss_partial(self.out, self.target_rgb, self.target_d, self.stats); n += 1
+        p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=self.u); n += 1
         reduce_stats(self.stats, self.pg)
         p.loss_finalize(self.stats, self.losses); n += 1
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,

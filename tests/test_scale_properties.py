@@ -54,6 +54,33 @@ def test_ray_kernel_equals_point_kernel_plus_compositor(n_samples_d, B):
     assert torch.allclose(w.sum(1), out.acc, atol=1e-5) and (out.acc <= 1.0 + 1e-5).all()
 
 
+@pytest.mark.parametrize('n_samples_d,B', [(32, 1), (32, 301), (117, 130), (117, 4096), (245, 9)])
+def test_fused_loss_statistics_equal_stand_alone_kernel(n_samples_d, B):
+    """nrt_render_fwd_stats (loss sums accumulated by the compositing warps) == nrt_render_fwd + nrt_loss_partial: identical
+    outputs, integer counts exact, squared-error sums to fp32 summation-order noise; repeatable bit for bit."""
+    from naruto_b200.field import RenderBuffers
+    cfg, plan, P = _plan(n_samples_d)
+    S = plan.S
+    o, d, rgb, td = _rays(B, seed=B + S)
+    u = torch.rand(B, S, generator=torch.Generator().manual_seed(1)).cuda()
+    a = RenderBuffers(B, S, 'cuda', per_sample=True, feat=True)
+    b = RenderBuffers(B, S, 'cuda', per_sample=True, feat=True)
+    sa, sb, sc = plan.new_stats('cuda'), plan.new_stats('cuda'), plan.new_stats('cuda')
+    plan.render_fwd(P, o, d, td, a, u=u)
+    plan.loss_partial(a, rgb, td, sa)
+    plan.render_fwd_stats(P, o, d, rgb, td, b, sb, u=u)
+    plan.render_fwd_stats(P, o, d, rgb, td, b, sc, u=u)
+    for k in ('rgb', 'depth', 'uncert', 'z_vals', 'raw', 'feat'):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    sa, sb, sc = sa[:12].cpu(), sb[:12].cpu(), sc[:12].cpu()
+    assert torch.equal(sb, sc), 'fused statistics must be deterministic'
+    for i in (0, 1, 2, 3, 4, 11):          # counts and the minimum: exact
+        assert sa[i] == sb[i], (i, sa[i], sb[i])
+    assert sb[0] == B and sb[4] == B * S
+    for i in range(5, 11):
+        assert abs(sa[i] - sb[i]) <= 2e-6 * abs(sa[i]) + 1e-12, (i, sa[i], sb[i])
+
+
 def test_empty_inputs():
     from naruto_b200.field import RenderBuffers
     cfg, plan, P = _plan(32)
