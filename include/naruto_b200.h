@@ -281,6 +281,29 @@ int nrt_selftest_umma_raw(const float* a_img, int32_t a_bytes, const float* b_im
                           int32_t a_mn, int32_t b_mn, int32_t a_lbo, int32_t a_sbo, int32_t a_kstep, int32_t b_lbo, int32_t b_sbo,
                           int32_t b_kstep, float* d, void* stream);
 
+/* ---- planner hand-off on the device ------------------------------------------------------------
+ * NarutoPlanner.uncertainty_aggregation_v2 (src/planner/naruto_planner.py:596-735) on device-resident volumes (the output
+ * of nrt_map_volumes): for every goal-space candidate g and target voxel j, collections[g,j] = uncert[target j] if the
+ * pair is inside the sensing range (min_dist < |g - j| < max_dist, voxels), the candidate is safe (one-voxel rim, SDF of
+ * its 7-stencil >= safe_sdf) and the 30-sample segment between them has SDF > 0 everywhere, else 0; aggre[g] = sum_j.
+ * uncert_vol / sdf_vol: dev [X,Y,Z]; dims = {X,Y,Z}; goal_pts: dev fp32 [n_goal,3] voxel coordinates (integers stored as
+ * floats, as the reference's goal_space_pts); topk_vxl: dev fp32 [k,3] (the reference's argpartition draw, or any
+ * selection); collections: dev [n_goal,k]; aggre: dev [n_goal]; n_valid (optional): dev int32, number of valid pairs
+ * (0 = the reference's "invalid goal space"). */
+int nrt_goal_aggregate(const float* uncert_vol, const float* sdf_vol, const int32_t* dims, const float* goal_pts, int64_t n_goal,
+                       const float* topk_vxl, int32_t k, float min_dist, float max_dist, float safe_sdf, float* collections,
+                       float* aggre, int32_t* n_valid, void* stream);
+
+/* ---- src/layers: ERP depth -> ERP radial distance ------------------------------------------------
+ * ERPDepth2Dist.forward (src/layers/erp_conversions.py:288-354; called per simulator step at
+ * src/simulator/habitat_simulator.py:143): 6 x E2P bilinear grid_sample -> depth2dist -> C2E nearest grid_sample, fused
+ * into one pass over the output panorama.  erp_depth / erp_dist: dev [H,W].  The three static grids are what the
+ * reference's constructor builds: c2e_grid dev [H,W,3] = C2E.grid (normalised x, y, face; src/layers/c2e.py:82-130),
+ * face_coor dev [6,s,s,2] = the six E2P.coor_xy (order F R B L U D), face_rays dev [3,s*s] = K^-1 [u,v,1] of
+ * Backprojection (src/layers/backprojection.py:31-82) with K = diag-ish(s/2). */
+int nrt_erp_depth2dist(const float* erp_depth, int32_t H, int32_t W, const float* c2e_grid, const float* face_coor,
+                       const float* face_rays, int32_t skybox_size, float* erp_dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,9 @@ int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float,
                 cudaStream_t);
 int launch_counter_add(int*, int, cudaStream_t);
 int launch_map_volumes(const NrtPlan*, const NrtParams*, const int*, float*, float*, cudaStream_t);
+int launch_goal_aggregate(const float*, const float*, const int*, const float*, int64_t, const float*, int, float, float, float,
+                          float*, float*, int*, int, cudaStream_t);
+int launch_erp_depth2dist(const float*, int, int, const float*, const float*, const float*, int, float*, int, cudaStream_t);
 int launch_camera_rays(int, int, float, float, float, float, float*, cudaStream_t);
 int launch_pack_frame(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
 int launch_valid_depth_count(const float*, int64_t, float, int*, cudaStream_t);
@@ -287,6 +290,33 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
   int sms = 148;
   return launch_adam(param, grad, exp_avg, exp_avg_sq, n, step, step_dev, lr, beta1, beta2, eps, weight_decay, zero_grad, sms,
                      (cudaStream_t)stream);
+}
+
+int nrt_goal_aggregate(const float* uncert_vol, const float* sdf_vol, const int32_t* dims, const float* goal_pts, int64_t n_goal,
+                       const float* topk_vxl, int32_t k, float min_dist, float max_dist, float safe_sdf, float* collections,
+                       float* aggre, int32_t* n_valid, void* stream) {
+  NRT_REQUIRE(dims && dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && n_goal >= 0 && k >= 0, "goal_aggregate sizes");
+  NRT_REQUIRE(n_goal == 0 || (uncert_vol && sdf_vol && goal_pts && aggre && (k == 0 || (topk_vxl && collections))),
+              "goal_aggregate arguments");
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+  }
+  return launch_goal_aggregate(uncert_vol, sdf_vol, dims, goal_pts, n_goal, topk_vxl, k, min_dist, max_dist, safe_sdf, collections,
+                               aggre, n_valid, sms, (cudaStream_t)stream);
+}
+
+int nrt_erp_depth2dist(const float* erp_depth, int32_t H, int32_t W, const float* c2e_grid, const float* face_coor,
+                       const float* face_rays, int32_t skybox_size, float* erp_dist, void* stream) {
+  NRT_REQUIRE(H >= 0 && W >= 0 && skybox_size >= 2, "erp_depth2dist sizes");
+  NRT_REQUIRE((int64_t)H * W == 0 || (erp_depth && c2e_grid && face_coor && face_rays && erp_dist), "erp_depth2dist arguments");
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+  }
+  return launch_erp_depth2dist(erp_depth, H, W, c2e_grid, face_coor, face_rays, skybox_size, erp_dist, sms, (cudaStream_t)stream);
 }
 
 int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream) {
