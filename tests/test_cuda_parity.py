@@ -260,3 +260,51 @@ def test_raw2outputs_and_sdf2weights(spec, dev):
     zz = torch.linspace(0, 5, 43, device=dev)[None]
     ww = m.sdf2weights(torch.full((1, 43), 0.3, device=dev), zz)
     assert (ww[0, zz[0] >= 0.1] == 0).all() and abs(ww.sum().item() - 1) < 1e-5
+
+
+# BASELINE.json configs[2] / configs[3] as parity cases ("the other configs are parity-test cases, not bench lines")
+APARTMENT_BOUND = [[-8.0, 8.0], [-6.0, 6.0], [-1.5, 3.5]]          # synthetic stand-in (no apartment_0 config ships)
+
+
+@pytest.mark.parametrize('name,bound,hash_size,n_samples_d,B', [
+    ('mp3d_large', 'MP3D_LARGE_BOUND', 21, 181, 41),      # 153.8 MB table, levels 0-7 dense, 192 samples/ray
+    ('apartment', APARTMENT_BOUND, 16, 32, 130),          # resolution_sdf 800: other level table, 43 samples/ray
+])
+def test_other_baseline_configs_vs_oracle(dev, name, bound, hash_size, n_samples_d, B):
+    """Training forward + backward of the CUDA path vs the oracle at the other configurations' bound / table size /
+    samples per ray (different dense-hashed split, level scales, uncertainty-grid dims)."""
+    from naruto_b200 import configs
+    from naruto_b200.scene_rep import JointEncodingNaruto
+    from oracle.make_golden import synth_rays
+    if isinstance(bound, str):
+        bound = getattr(configs, bound)
+    sp = no.office0_spec(n_samples_d=n_samples_d, log2_hashmap_size=hash_size, bound=bound)
+    P = no.init_params(sp, seed=12, grid_range=0.3, uncert_jitter=1.0)
+    o, d, rgb, td = synth_rays(sp, B, seed=21)
+    u = torch.rand(B, sp.n_samples, generator=torch.Generator().manual_seed(4))
+    Pg = P.clone(requires_grad=True)
+    ret_o = no.forward_train(o, d, rgb, td, Pg, sp, u=u)
+    no.total_loss(ret_o, sp).backward()
+    cfg = configs.replica_office0(n_samples_d=n_samples_d, hash_size=hash_size, bound=bound)
+    m = JointEncodingNaruto(cfg, torch.tensor(sp.bound)).to(dev)
+    m.get_uncert_grid(0.1)
+    with torch.no_grad():
+        m.embed_fn.params.copy_(P.grid)
+        m.decoder.sdf_net.model[0].weight.copy_(P.w1)
+        m.decoder.sdf_net.model[2].weight.copy_(P.w2)
+        m.decoder.color_net.model[0].weight.copy_(P.w3)
+        m.decoder.color_net.model[2].weight.copy_(P.w4)
+        m.uncert_grid.copy_(P.uncert_grid)
+    m.train()
+    ret = m.forward(o.to(dev), d.to(dev), rgb.to(dev), td.to(dev), u=u.to(dev))
+    rays_close(ret['rgb'], ret_o['rgb'].detach().numpy(), name + ' rgb')
+    rays_close(ret['depth'], ret_o['depth'].detach().numpy(), name + ' depth')
+    for k in ('rgb_loss', 'depth_loss', 'sdf_loss', 'fs_loss', 'uncert_loss'):
+        close(ret[k], ret_o[k], 2e-4, name + ' ' + k)
+    loss = (sp.rgb_weight * ret['rgb_loss'] + sp.depth_weight * ret['depth_loss'] + sp.sdf_weight * ret['sdf_loss']
+            + sp.fs_weight * ret['fs_loss'] + sp.uncert_weight * ret['uncert_loss'])
+    loss.backward()
+    close(m.decoder.sdf_net.model[0].weight.grad, Pg.w1.grad, 2e-3, name + ' w1 grad')
+    close(m.decoder.color_net.model[2].weight.grad, Pg.w4.grad, 2e-3, name + ' w4 grad')
+    close(m.embed_fn.params.grad, Pg.grid.grad, 2e-3, name + ' grid grad')
+    close(m.uncert_grid.grad, Pg.uncert_grid.grad, 2e-3, name + ' uncert grad')
