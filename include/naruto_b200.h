@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define NRT_ABI_VERSION 1
+#define NRT_ABI_VERSION 2
 
 typedef enum NrtStatus {
   NRT_OK = 0,
@@ -111,6 +111,9 @@ typedef struct NrtRenderOut {
   float* raw;         /* dev [B,S,5] = rgb logits(3), sdf, raw uncertainty */
   float* weights;     /* dev [B,S] */
   float* feat;        /* dev [B*S,32] hash features, saved for nrt_render_bwd (training) */
+  uint32_t* masks;    /* dev [B*S,2] ReLU masks of the two hidden layers (bit j = unit j active), saved for nrt_render_bwd:
+                       * with them the backward recomputes activations in single-pass TF32 (they only feed the tf32
+                       * weight-gradient operands) instead of 3xTF32; optional (NULL: masks are recomputed exactly) */
 } NrtRenderOut;
 
 #define NRT_N_LOSS 8

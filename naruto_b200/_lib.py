@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libnaruto_b200.so')
 
-NRT_ABI_VERSION = 1
+NRT_ABI_VERSION = 2
 N_LOSS = 8
 N_STATS = 16
 N_STATS_SUM = 11
@@ -39,7 +39,7 @@ class NrtGrads(C.Structure):
 
 
 class NrtRenderOut(C.Structure):
-    _fields_ = [(n, c_fp) for n in ('rgb', 'depth', 'depth_var', 'acc', 'disp', 'uncert', 'z_vals', 'raw', 'weights', 'feat')]
+    _fields_ = [(n, c_fp) for n in ('rgb', 'depth', 'depth_var', 'acc', 'disp', 'uncert', 'z_vals', 'raw', 'weights', 'feat', 'masks')]
 
 
 # name -> (restype, argtypes); every symbol include/naruto_b200.h declares

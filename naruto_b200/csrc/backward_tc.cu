@@ -45,8 +45,8 @@
 #define BWD_THREADS 512            // 256 scatter threads (warps 0..7) + 256 MLP threads (warps 8..15)
 #define RING_DF_FLOATS (8 * 128 * 4)          // dfeat of one tile, chunk-major [8 chunks][128 rows][4]
 #define RING_STAGE_FLOATS (RING_DF_FLOATS + 4 * 128)   // + x0[128] x1[128] x2[128] active[128]
-#define BAR_FULL 2                 // named barriers: hand-over slot filled / drained
-#define BAR_EMPTY 3
+#define BAR_FULL(s) (2 + 2 * (s))   // named barriers: hand-over stage s filled / drained
+#define BAR_EMPTY(s) (3 + 2 * (s))
 #define XT_FLOATS (32 * XT_ROWS * 4)
 #define YT_FLOATS (32 * YT_ROWS * 4 + 160)     // the MMA reads 128 rows per chunk: slack behind the last chunk
 
@@ -64,13 +64,15 @@ __device__ __forceinline__ void put_split_bw(float* blk, int o, float v) {
 // 2 steps on the medium ones; DevLevel::agg) that sit in the same cell, and only the first lane of each run issues the
 // reductions.
 // ---------------------------------------------------------------------------------------------
+template <int NSTG>
 __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* __restrict__ s_lv, const float* __restrict__ ring,
                                               float2* __restrict__ dgrid, int64_t n_tiles) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_tiles = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   for (int k = 0; k < my_tiles; ++k) {
-    const float* stage = ring;
-    bar_sync(BAR_FULL, BWD_THREADS);
+    const int stg = k % NSTG;
+    const float* stage = ring + stg * RING_STAGE_FLOATS;
+    bar_sync(BAR_FULL(stg), BWD_THREADS);
     const float* xs = stage + RING_DF_FLOATS;
     // iteration = (block of 32 consecutive rows, one of this warp's two levels)
 #pragma unroll 1
@@ -124,18 +126,48 @@ __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* 
         }
       }
     }
-    if (k + 1 < my_tiles) bar_arrive(BAR_EMPTY, BWD_THREADS);
+    if (k + NSTG < my_tiles) bar_arrive(BAR_EMPTY(stg), BWD_THREADS);
   }
 }
 
+// SAVED: the forward pass saved the ReLU masks of both hidden layers (NrtRenderOut::masks).  The network is piecewise linear,
+// so with the masks given every DATA gradient (dfeat, d uncert) is independent of the recomputed activation values; those
+// only feed the tf32-rounded operands of the weight-gradient GEMM.  The two recompute phases then run single-pass TF32 on the
+// hi pieces alone: a third of the MMAs, no lo staging, no lo copy of W1 / W23 in shared memory -- which makes room for a
+// second hand-over stage, so the MLP group no longer waits for the scatter warps to drain the previous tile.
+template <bool SAVED>
 __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
                                                                       const PointSource src, int64_t n_pts,
                                                                       const float* __restrict__ feat,
+                                                                      const uint32_t* __restrict__ masks,
                                                                       const float* __restrict__ draw, float* __restrict__ dfeat,
                                                                       const NrtGrads grads) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int NSTG = SAVED ? 2 : 1;
   float* rest;
-  TileCtx c = cta_prologue<BT_COLS>(smem_raw, prm, &rest);
+  TileCtx c;
+  if (SAVED) {
+    // cta_prologue() with the hi pieces of W1 / W23 only
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 8);
+    float* sw = reinterpret_cast<float*>(smem_raw + TC_SMEM_HEADER);
+    if ((threadIdx.x >> 5) == 0) {
+      if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+      }
+      __syncwarp();
+      tmem_alloc<BT_COLS>(slot);
+    }
+    load_weights_hi(sw, prm);
+    c.bar = bar;
+    c.phase = 0u;
+    c.w_hi = smem_u32(sw);
+    c.w_lo = 0u;
+    rest = sw + FW_W4;
+  } else {
+    c = cta_prologue<BT_COLS>(smem_raw, prm, &rest);
+  }
   float* bw = rest;                       // backward weights hi | lo
   float* w4s = bw + 2 * BW_FLOATS;        // w4 as stored [3][32] (+ pad)
   float* xt = w4s + 128;
@@ -177,7 +209,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
   // Warp roles: the SM's issue arbiter favours high warp ids, so the latency-critical MLP chain takes warps 8..15 and
   // the throughput-bound scatter takes warps 0..7.
   if (t < TC_THREADS) {
-    scatter_warps(P, s_lv, ring, reinterpret_cast<float2*>(grads.grid), n_tiles);
+    scatter_warps<NSTG>(P, s_lv, ring, reinterpret_cast<float2*>(grads.grid), n_tiles);
   } else {
   int k = 0;                      // tiles done by this CTA
   for (int64_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x, ++k) {
@@ -185,7 +217,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
     const bool active = pt < n_pts;
     float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     float dc[3] = {0.f, 0.f, 0.f}, dsdf = 0.f, du = 0.f;
+    unsigned m1 = 0u, m3 = 0u;        // ReLU masks of this half's 16 units of either hidden layer
     if (active) {
+      if (SAVED) {
+        const uint2 mk = __ldg(reinterpret_cast<const uint2*>(masks) + pt);
+        m1 = (mk.x >> (16 * half)) & 0xffffu;
+        m3 = (mk.y >> (16 * half)) & 0xffffu;
+      }
       fetch_point(P, src, pt, x0, x1, x2);
       const float* g = draw + pt * 5;
       dc[0] = __ldg(g);
@@ -220,7 +258,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
         xcol[(XR_HASH + 16 * half + i) * 4] = hi[i];
       }
       tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
-      tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
+      if (!SAVED) tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
     }
 #pragma unroll 1
     for (int d = 2 * half; d < 2 + half; ++d) {
@@ -235,11 +273,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
         xcol[(XR_OB + 16 * d + i) * 4] = hi[i];
       }
       tmem_st16(c.lane_tb + TC_AHI + TA_OB + 16 * d, hi);
-      tmem_st16(c.lane_tb + TC_ALO + TA_OB + 16 * d, lo);
+      if (!SAVED) tmem_st16(c.lane_tb + TC_ALO + TA_OB + 16 * d, lo);
     }
     // ---- recompute layer 1 ----
-    run_layer<80, 32>(c, TA_X0, c.w_hi + FW_W1 * 4, c.w_lo + FW_W1 * 4);
-    unsigned m1 = 0u;                 // ReLU mask of this half's 16 hidden units
+    if (SAVED) run_layer_1p<80, 32>(c, TA_X0, c.w_hi + FW_W1 * 4);
+    else run_layer<80, 32>(c, TA_X0, c.w_hi + FW_W1 * 4, c.w_lo + FW_W1 * 4);
     {
       float h[16];
       tmem_ld16(c.lane_tb + TC_ACC + 16 * half, h);
@@ -248,16 +286,17 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const float v = fmaxf(h[i], 0.f);
-        if (v > 0.f) m1 |= 1u << i;
+        if (!SAVED && v > 0.f) m1 |= 1u << i;
         hi[i] = tf32_hi(v);
         lo[i] = v - hi[i];
         xcol[(XR_H1 + 16 * half + i) * 4] = hi[i];
       }
       tmem_st16(c.lane_tb + TC_AHI + TA_X0 + 16 * half, hi);
-      tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
+      if (!SAVED) tmem_st16(c.lane_tb + TC_ALO + TA_X0 + 16 * half, lo);
     }
     // ---- recompute phase 2 on [h1 | oneblob]: o = [sdf, geo] (columns 0..15) and a3 (columns 16..47) ----
-    run_layer<80, 48>(c, TA_X0, c.w_hi + FW_W23 * 4, c.w_lo + FW_W23 * 4);
+    if (SAVED) run_layer_1p<80, 48>(c, TA_X0, c.w_hi + FW_W23 * 4);
+    else run_layer<80, 48>(c, TA_X0, c.w_hi + FW_W23 * 4, c.w_lo + FW_W23 * 4);
     {
       float o[8], a3[16];
       tmem_ld8(c.lane_tb + TC_ACC + 8 * half, o);
@@ -277,7 +316,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
         const float hv = fmaxf(a3[i], 0.f);
         xcol[(XR_H3 + j) * 4] = tf32_hi(hv);
         const float d = dc[0] * w4s[j] + dc[1] * w4s[32 + j] + dc[2] * w4s[64 + j];
-        const float v = hv > 0.f ? d : 0.f;
+        const float v = (SAVED ? ((m3 >> i) & 1u) != 0u : hv > 0.f) ? d : 0.f;
         hi[i] = tf32_hi(v);
         lo[i] = v - hi[i];
         ycol[(YR_DA3 + j) * 4] = hi[i];
@@ -343,8 +382,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
           reinterpret_cast<float4*>(dfeat + pt * NRT_ENC + 16 * half)[q] = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
       }
       // hand the tile to the scatter warps through the ring
-      float* stage = ring;
-      if (k >= 1) bar_sync(BAR_EMPTY, BWD_THREADS);
+      const int stg = k % NSTG;
+      float* stage = ring + stg * RING_STAGE_FLOATS;
+      if (k >= NSTG) bar_sync(BAR_EMPTY(stg), BWD_THREADS);
 #pragma unroll
       for (int q = 0; q < 4; ++q) sts4(stage + ((4 * half + q) * 128 + row) * 4, df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
       if (half == 0) {
@@ -354,7 +394,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
         xs[256 + row] = x2;
         xs[384 + row] = active ? 1.0f : 0.0f;
       }
-      bar_arrive(BAR_FULL, BWD_THREADS);
+      bar_arrive(BAR_FULL(stg), BWD_THREADS);
     }
     // uncertainty grid: raw[...,4] is the trilinear sample itself
     if (half == 1 && active && grads.uncert && du != 0.f) {
@@ -403,22 +443,28 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
   cta_epilogue<BT_COLS>(c);
 }
 
-size_t decode_bwd_tc_smem() {
-  return TC_SMEM_WEIGHTS + (size_t)(2 * BW_FLOATS + 128 + XT_FLOATS + YT_FLOATS + RING_STAGE_FLOATS) * sizeof(float);
+size_t decode_bwd_tc_smem(bool saved) {
+  const size_t fw = saved ? (size_t)FW_W4 : (size_t)2 * FW_FLOATS;
+  return TC_SMEM_HEADER + (fw + 2 * BW_FLOATS + 128 + XT_FLOATS + YT_FLOATS + (saved ? 2 : 1) * RING_STAGE_FLOATS) * sizeof(float);
 }
 
 int launch_decode_bwd(const NrtPlan* plan, const NrtParams* prm, const PointSource& src, int64_t n_pts, const float* feat,
-                      const float* draw, float* dfeat, const NrtGrads* grads, cudaStream_t st) {
+                      const uint32_t* masks, const float* draw, float* dfeat, const NrtGrads* grads, cudaStream_t st) {
   if (n_pts == 0) return NRT_OK;
-  const size_t smem = decode_bwd_tc_smem();
+  const bool saved = masks != nullptr;
+  const size_t smem = decode_bwd_tc_smem(saved);
   static bool attr_set = false;
   if (!attr_set) {
-    NRT_CUDA_CHECK(cudaFuncSetAttribute(decode_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NRT_CUDA_CHECK(cudaFuncSetAttribute(decode_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_bwd_tc_smem(true)));
+    NRT_CUDA_CHECK(cudaFuncSetAttribute(decode_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_bwd_tc_smem(false)));
     attr_set = true;
   }
   const int64_t tiles = (n_pts + 127) / 128;
   const int blocks = (int)(tiles < plan->sm_count ? tiles : plan->sm_count);
-  decode_bwd_tc_kernel<<<blocks, BWD_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, draw, dfeat, *grads);
+  if (saved)
+    decode_bwd_tc_kernel<true><<<blocks, BWD_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, masks, draw, dfeat, *grads);
+  else
+    decode_bwd_tc_kernel<false><<<blocks, BWD_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, nullptr, draw, dfeat, *grads);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

@@ -169,8 +169,13 @@ __device__ __forceinline__ LevelPos level_corners(const DevLevel& L, float x0, f
     for (int c = 0; c < 8; ++c) idx[c] = ((p.g[0] + (c & 1)) ^ hyz[c >> 1]) & m;
   } else {
     const uint32_t base = p.g[0] + p.g[1] * L.res + p.g[2] * L.res2;
+    if (base < L.lim) {                   // whole cell in range: % size is the identity (DevLevel::lim)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) idx[c] = mod_size(L, base + (c & 1) + ((c >> 1) & 1) * L.res + (c >> 2) * L.res2);
+      for (int c = 0; c < 8; ++c) idx[c] = base + (c & 1) + ((c >> 1) & 1) * L.res + (c >> 2) * L.res2;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) idx[c] = mod_size(L, base + (c & 1) + ((c >> 1) & 1) * L.res + (c >> 2) * L.res2);
+    }
   }
   return p;
 }

@@ -35,7 +35,8 @@
 template <bool COLOR>
 __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const float2* __restrict__ grid,
                                             const float* __restrict__ ug, bool active, float x0, float x1, float x2,
-                                            float* __restrict__ feat_out, PointOut& out) {
+                                            float* __restrict__ feat_out, PointOut& out,
+                                            uint16_t* __restrict__ mask_out = nullptr) {
   const int half = tc_half();
   // ---- encodings -> TMEM ----
   // two hash levels per iteration, gathered pair-cooperatively (common.cuh: gather_levels_paired); rolled loops keep the
@@ -62,8 +63,13 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
     float h[16];
     tmem_ld16(c.lane_tb + TC_ACC + 16 * half, h);
     tmem_ld_wait();
+    uint32_t m = 0u;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+    for (int j = 0; j < 16; ++j) {
+      h[j] = fmaxf(h[j], 0.f);
+      if (h[j] > 0.f) m |= 1u << j;
+    }
+    if (mask_out) mask_out[half] = (uint16_t)m;        // NrtRenderOut::masks[pt] = {m1, m3}, this half's 16 bits of m1
     stage16(c, TA_X0 + 16 * half, h);
   }
   // ---- phase 2 on [h1 | oneblob]: o = W2 h1 (columns 0..15) and a3 = W23 h1 + W3_ob oneblob (columns 16..47) ----
@@ -73,8 +79,13 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
     float h[16];
     tmem_ld16(c.lane_tb + TC_ACC + 16 + 16 * half, h);
     tmem_ld_wait();
+    uint32_t m = 0u;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+    for (int j = 0; j < 16; ++j) {
+      h[j] = fmaxf(h[j], 0.f);
+      if (h[j] > 0.f) m |= 1u << j;
+    }
+    if (mask_out) mask_out[2 + half] = (uint16_t)m;
     stage16(c, TA_X0 + 16 * half, h);
     // ---- phase 3: rgb logits = W4 relu(a3) ----
     run_layer<32, 16>(c, TA_X0, c.w_hi + FW_W4 * 4, c.w_lo + FW_W4 * 4);
@@ -228,7 +239,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(const __gr
       }
       PointOut po;
       decode_tile<true>(P, c, grid, prm.uncert, active, x0, x1, x2,
-                        (out.feat && active) ? out.feat + (r0 * S + pl) * NRT_ENC : nullptr, po);
+                        (out.feat && active) ? out.feat + (r0 * S + pl) * NRT_ENC : nullptr, po,
+                        (out.masks && active) ? reinterpret_cast<uint16_t*>(out.masks) + (r0 * S + pl) * 4 : nullptr);
       if (active) {
         float* r = s_raw + pl * 5;
         if (half == 0) {

@@ -191,13 +191,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
         if (cnt + WS_NST < total_tiles) bar_arrive(WS_BAR_EMPTY(g, st), WS_SUB);     // someone will refill this stage
         // ---- phase 1: h1 = relu(W1 [hash | oneblob]) ----
         ws_run_layer<80, 32>(c, g, issuer, TA_X0, c.w_hi + FW_W1 * 4, c.w_lo + FW_W1 * 4);
+        uint32_t m1 = 0u, m3 = 0u;                                     // ReLU masks, saved for the backward pass
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           float h[16];
           tmem_ld16(c.lane_tb + TC_ACC + 16 * q, h);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+          for (int j = 0; j < 16; ++j) {
+            h[j] = fmaxf(h[j], 0.f);
+            if (h[j] > 0.f) m1 |= 1u << (16 * q + j);
+          }
           stage16(c, TA_X0 + 16 * q, h);
         }
         // ---- phase 2 on [h1 | oneblob]: o = W2 h1 (columns 0..15) and a3 = W23 h1 + W3_ob oneblob (columns 16..47) ----
@@ -210,9 +214,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
           tmem_ld16(c.lane_tb + TC_ACC + 16 + 16 * q, h);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+          for (int j = 0; j < 16; ++j) {
+            h[j] = fmaxf(h[j], 0.f);
+            if (h[j] > 0.f) m3 |= 1u << (16 * q + j);
+          }
           stage16(c, TA_X0 + 16 * q, h);
         }
+        if (out.masks && pl < npts) reinterpret_cast<uint2*>(out.masks)[r0 * S + pl] = make_uint2(m1, m3);
         // ---- phase 3: rgb logits = W4 relu(a3) ----
         ws_run_layer<32, 16>(c, g, issuer, TA_X0, c.w_hi + FW_W4 * 4, c.w_lo + FW_W4 * 4);
         float r4[4];

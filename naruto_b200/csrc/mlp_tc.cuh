@@ -92,6 +92,17 @@ __device__ __forceinline__ void issue_layer(const TileCtx& c, int a_col, uint32_
   for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, ah + 8 * ks, bl + (uint64_t)(2 * N * ks), idesc, true);
 }
 
+// single pass (A_hi * B_hi): plain TF32, for values that are rounded to tf32 afterwards anyway
+template <int K, int N>
+__device__ __forceinline__ void issue_layer_1p(const TileCtx& c, int a_col, uint32_t wh) {
+  constexpr uint32_t idesc = idesc_tf32(128, N, 0, 0);
+  const uint32_t d = c.tb + TC_ACC;
+  const uint32_t ah = c.tb + TC_AHI + a_col;
+  const uint64_t bh = smem_desc(wh, N * 16, 128);
+#pragma unroll
+  for (int ks = 0; ks < K / 8; ++ks) mma_tf32_ts(d, ah + 8 * ks, bh + (uint64_t)(2 * N * ks), idesc, ks > 0);
+}
+
 // The 256 MLP threads (threads 0..255 of the CTA) meet on named barrier 1, so a CTA may carry extra warps with other roles.
 #define TC_BAR_MLP 1
 __device__ __forceinline__ void tc_sync() { bar_sync(TC_BAR_MLP, TC_THREADS); }
@@ -125,6 +136,34 @@ __device__ __forceinline__ void run_layer(TileCtx& c, int a_col, uint32_t wh, ui
     }
   }
   layer_wait(c);
+}
+
+template <int K, int N>
+__device__ __forceinline__ void run_layer_1p(TileCtx& c, int a_col, uint32_t wh) {
+  layer_publish();
+  if (tc_issuer_warp()) {
+    tc_fence_after();
+    if (elect_one()) {
+      issue_layer_1p<K, N>(c, a_col, wh);
+      mma_commit(c.bar);
+    }
+  }
+  layer_wait(c);
+}
+
+// forward weights, hi pieces of W1 and W23 only (single-pass recompute of the backward kernel): FW_W4 floats
+__device__ __forceinline__ void load_weights_hi(float* sw, const NrtParams& prm) {
+  for (int i = threadIdx.x; i < 80 * 32; i += blockDim.x) {
+    const int j = i / 80, k = i % 80;
+    sw[FW_W1 + ((k >> 2) * 32 + j) * 4 + (k & 3)] = tf32_hi(__ldg(prm.w1 + i));
+  }
+  for (int i = threadIdx.x; i < 48 * 80; i += blockDim.x) {
+    const int n = i / 80, k = i % 80;
+    float v;
+    if (n < 16) v = k < 32 ? __ldg(prm.w2 + n * 32 + k) : 0.f;
+    else v = k < 32 ? w23_at(prm, n - 16, k) : __ldg(prm.w3 + (n - 16) * 63 + (k - 32));
+    sw[FW_W23 + ((k >> 2) * 48 + n) * 4 + (k & 3)] = tf32_hi(v);
+  }
 }
 
 // stage 16 / 8 consecutive A columns (hi and lo pieces) of this thread's row

@@ -62,10 +62,12 @@ class RenderBuffers:
         self.raw = torch.empty(B, S, 5, **f) if per_sample else None
         self.weights = torch.empty(B, S, **f) if weights else None
         self.feat = torch.empty(B * S, ENC_DIMS, **f) if feat else None
+        self.masks = torch.empty(B * S, 2, dtype=torch.int32, device=device) if feat else None      # ReLU masks, saved with feat
 
     def c_struct(self):
         return L.NrtRenderOut(L.ptr(self.rgb), L.ptr(self.depth), L.ptr(self.depth_var), L.ptr(self.acc), L.ptr(self.disp),
-                              L.ptr(self.uncert), L.ptr(self.z_vals), L.ptr(self.raw), L.ptr(self.weights), L.ptr(self.feat))
+                              L.ptr(self.uncert), L.ptr(self.z_vals), L.ptr(self.raw), L.ptr(self.weights), L.ptr(self.feat),
+                              L.ptr(self.masks))
 
 
 class FieldPlan:
