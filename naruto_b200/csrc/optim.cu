@@ -22,24 +22,26 @@ __device__ __forceinline__ float lattice_coord(const DevPlan& P, int d, int i, c
   return normalise1(P, d, p);
 }
 
-// pass 1: hash features of every lattice point -> F[m^3][16] (float2), thread = (point, level)
+// Both passes run with blockIdx.y = level and thread = lattice point (z index fastest), so a warp holds 32 neighbouring
+// points of ONE level: level constants are uniform (constant bank, no shared-memory table), neighbouring points share or
+// adjoin cells (L1 hits on the gather, reductions into neighbouring sectors), and the feature workspace F[level][point] is
+// read and written coalesced.  (The first version used thread = (point, level) with the level fastest: 16 different level
+// tables per warp, a bank-conflicted shared-memory level table and a strided workspace -- 14 + 31 us per iteration.)
+
+// pass 1: hash features of every lattice point -> F[16][m^3] (float2)
 __global__ void __launch_bounds__(256) smooth_encode_kernel(const __grid_constant__ DevPlan P, const float2* __restrict__ grid,
                                                             const float* __restrict__ rnd, const LatticeSpec ls,
                                                             float2* __restrict__ F) {
-  __shared__ DevLevel s_lv[NRT_L];
-  if (threadIdx.x < NRT_L) s_lv[threadIdx.x] = P.lv[threadIdx.x];
-  __syncthreads();
-  const int n = ls.n;
-  const int m = n - 1;
-  int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t pt = tt >> 4;
-  int l = (int)(tt & 15);
-  if (pt >= (int64_t)m * m * m) return;
-  int k = (int)(pt % m), j = (int)((pt / m) % m), i = (int)(pt / ((int64_t)m * m));
-  float x0 = lattice_coord(P, 0, i, rnd, ls);
-  float x1 = lattice_coord(P, 1, j, rnd, ls);
-  float x2 = lattice_coord(P, 2, k, rnd, ls);
-  F[pt * NRT_L + l] = level_gather(s_lv[l], grid, x0, x1, x2);
+  const int l = blockIdx.y;
+  const int m = ls.n - 1;
+  const int64_t total = (int64_t)m * m * m;
+  const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= total) return;
+  const int k = (int)(pt % m), j = (int)((pt / m) % m), i = (int)(pt / ((int64_t)m * m));
+  const float x0 = lattice_coord(P, 0, i, rnd, ls);
+  const float x1 = lattice_coord(P, 1, j, rnd, ls);
+  const float x2 = lattice_coord(P, 2, k, rnd, ls);
+  F[(int64_t)l * total + pt] = level_gather(P.lv[l], grid, x0, x1, x2);
 }
 
 // pass 2: TV loss + its gradient scattered straight into the table.
@@ -47,33 +49,30 @@ __global__ void __launch_bounds__(256) smooth_encode_kernel(const __grid_constan
 __global__ void __launch_bounds__(256) smooth_tv_bwd_kernel(const __grid_constant__ DevPlan P, const float* __restrict__ rnd,
                                                             const LatticeSpec ls, const float2* __restrict__ F,
                                                             float loss_scale, float* __restrict__ loss, float2* __restrict__ dgrid) {
-  __shared__ DevLevel s_lv[NRT_L];
   __shared__ float s_red[8];
-  if (threadIdx.x < NRT_L) s_lv[threadIdx.x] = P.lv[threadIdx.x];
-  __syncthreads();
+  const int l = blockIdx.y;
   const int n = ls.n;
   const int m = n - 1;
   const int64_t total = (int64_t)m * m * m;
-  int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t pt = tt >> 4;
-  int l = (int)(tt & 15);
+  const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float2* __restrict__ Fl = F + (int64_t)l * total;
   float tv = 0.f;
   if (pt < total) {
-    int idx[3] = {(int)(pt / ((int64_t)m * m)), (int)((pt / m) % m), (int)(pt % m)};
+    const int idx[3] = {(int)(pt / ((int64_t)m * m)), (int)((pt / m) % m), (int)(pt % m)};
     const int64_t stride[3] = {(int64_t)m * m, m, 1};
-    const float2 f = F[pt * NRT_L + l];
+    const float2 f = Fl[pt];
     float2 g = make_float2(0.f, 0.f);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       if (idx[d] + 1 < m) {
-        float2 q = F[(pt + stride[d]) * NRT_L + l];
-        float ex = f.x - q.x, ey = f.y - q.y;
+        const float2 q = Fl[pt + stride[d]];
+        const float ex = f.x - q.x, ey = f.y - q.y;
         tv += ex * ex + ey * ey;      // each edge counted once, at its lower end
         g.x += ex;
         g.y += ey;
       }
       if (idx[d] > 0) {
-        float2 q = F[(pt - stride[d]) * NRT_L + l];
+        const float2 q = Fl[pt - stride[d]];
         g.x += f.x - q.x;
         g.y += f.y - q.y;
       }
@@ -82,17 +81,16 @@ __global__ void __launch_bounds__(256) smooth_tv_bwd_kernel(const __grid_constan
     g.x *= 2.0f * inv * loss_scale;
     g.y *= 2.0f * inv * loss_scale;
     if (dgrid && (g.x != 0.f || g.y != 0.f)) {
-      float x0 = lattice_coord(P, 0, idx[0], rnd, ls);
-      float x1 = lattice_coord(P, 1, idx[1], rnd, ls);
-      float x2 = lattice_coord(P, 2, idx[2], rnd, ls);
-      const DevLevel& L = s_lv[l];
-      LevelPos p = level_pos(L, x0, x1, x2);
+      const float x0 = lattice_coord(P, 0, idx[0], rnd, ls);
+      const float x1 = lattice_coord(P, 1, idx[1], rnd, ls);
+      const float x2 = lattice_coord(P, 2, idx[2], rnd, ls);
+      const DevLevel& L = P.lv[l];
+      uint32_t e[8];
+      float w[8];
+      level_corners(L, x0, x1, x2, e, w);
+      float2* base = dgrid + L.offset;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t e = level_index(L, p.g[0] + (c & 1), p.g[1] + ((c >> 1) & 1), p.g[2] + ((c >> 2) & 1));
-        float w = corner_weight(p, c);
-        red_add_f2(dgrid + L.offset + e, w * g.x, w * g.y);
-      }
+      for (int c = 0; c < 8; ++c) red_add_f2(base + e[c], w[c] * g.x, w[c] * g.y);
     }
     tv *= inv;
   }
@@ -109,8 +107,8 @@ __global__ void __launch_bounds__(256) smooth_tv_bwd_kernel(const __grid_constan
 int launch_smooth(const NrtPlan* plan, const float* grid, const float* rnd6, int n, double voxel, double margin,
                   float loss_scale, float* loss, float* dgrid, void* workspace, cudaStream_t st) {
   const int m = n - 1;
-  const int64_t threads = (int64_t)m * m * m * NRT_L;
-  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  const int64_t pts = (int64_t)m * m * m;
+  const dim3 blocks((unsigned)((pts + 255) / 256), NRT_L);
   float2* F = reinterpret_cast<float2*>(workspace);
   LatticeSpec ls{n, (float)voxel, (float)((double)(n - 1) * voxel), (float)margin, (float)(2.0 * margin)};
   NRT_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), st));
