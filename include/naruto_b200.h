@@ -297,6 +297,24 @@ int nrt_goal_aggregate(const float* uncert_vol, const float* sdf_vol, const int3
                        const float* topk_vxl, int32_t k, float min_dist, float max_dist, float safe_sdf, float* collections,
                        float* aggre, int32_t* n_valid, void* stream);
 
+/* ---- iso-surface extraction ---------------------------------------------------------------------
+ * mcubes.marching_cubes(volume, isovalue, truncation) of the reference
+ * (third_parties/coslam/external/NumpyMarchingCubes/marching_cubes/src/marching_cubes.cpp:418-462 behind _mcubes.pyx:20-25;
+ * called by save_mesh / save_uncert_mesh at src/slam/coslam/coslam_utils.py:145): dual-grid marching cubes with
+ * truncation / jump thresholds, then an order-dependent vertex merge and face clean-up.  The O(n^3) part (corner means,
+ * cell classification, prefix sum, vertex interpolation) runs on the device, the merge over the compacted triangle soup on
+ * the host; vertices and faces equal the reference's, index for index.
+ * volume: dev fp32 [nx,ny,nz] (the values the reference reads, which are float32 sweeps widened to double);
+ * workspace: dev scratch of nrt_mc_workspace_bytes() bytes.  This is an export path: nrt_mc_extract synchronises the stream
+ * and allocates the (result-sized) soup buffer itself.  The result handle owns host arrays: vertices double [V,3], faces
+ * uint64 [F,3] (the reference's dtypes); copy them out, then free the handle. */
+int64_t nrt_mc_workspace_bytes(int32_t nx, int32_t ny, int32_t nz);
+int nrt_mc_extract(const float* volume, int32_t nx, int32_t ny, int32_t nz, float isovalue, float truncation, void* workspace,
+                   void* stream, void** result);
+int nrt_mc_result_sizes(void* result, int64_t* n_vertices, int64_t* n_faces);
+int nrt_mc_result_copy(void* result, double* vertices, uint64_t* faces);
+void nrt_mc_result_free(void* result);
+
 /* ---- src/layers: ERP depth -> ERP radial distance ------------------------------------------------
  * ERPDepth2Dist.forward (src/layers/erp_conversions.py:288-354; called per simulator step at
  * src/simulator/habitat_simulator.py:143): 6 x E2P bilinear grid_sample -> depth2dist -> C2E nearest grid_sample, fused

@@ -30,6 +30,11 @@ int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float,
                 cudaStream_t);
 int launch_counter_add(int*, int, cudaStream_t);
 int launch_map_volumes(const NrtPlan*, const NrtParams*, const int*, float*, float*, cudaStream_t);
+int64_t mc_workspace_bytes(int, int, int);
+int mc_extract(const float*, int, int, int, float, float, void*, cudaStream_t, void**);
+void mc_sizes(void*, int64_t*, int64_t*);
+void mc_copy(void*, double*, unsigned long long*);
+void mc_release(void*);
 int launch_goal_aggregate(const float*, const float*, const int*, const float*, int64_t, const float*, int, float, float, float,
                           float*, float*, int*, int, cudaStream_t);
 int launch_erp_depth2dist(const float*, int, int, const float*, const float*, const float*, int, float*, int, cudaStream_t);
@@ -290,6 +295,34 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
   int sms = 148;
   return launch_adam(param, grad, exp_avg, exp_avg_sq, n, step, step_dev, lr, beta1, beta2, eps, weight_decay, zero_grad, sms,
                      (cudaStream_t)stream);
+}
+
+int64_t nrt_mc_workspace_bytes(int32_t nx, int32_t ny, int32_t nz) {
+  if (nx < 0 || ny < 0 || nz < 0) return 0;
+  return mc_workspace_bytes(nx, ny, nz);
+}
+
+int nrt_mc_extract(const float* volume, int32_t nx, int32_t ny, int32_t nz, float isovalue, float truncation, void* workspace,
+                   void* stream, void** result) {
+  NRT_REQUIRE(result && nx >= 0 && ny >= 0 && nz >= 0, "mc_extract sizes");
+  NRT_REQUIRE((int64_t)nx * ny * nz == 0 || (volume && workspace), "mc_extract arguments");
+  return mc_extract(volume, nx, ny, nz, isovalue, truncation, workspace, (cudaStream_t)stream, result);
+}
+
+int nrt_mc_result_sizes(void* result, int64_t* n_vertices, int64_t* n_faces) {
+  NRT_REQUIRE(result && n_vertices && n_faces, "mc_result_sizes arguments");
+  mc_sizes(result, n_vertices, n_faces);
+  return NRT_OK;
+}
+
+int nrt_mc_result_copy(void* result, double* vertices, uint64_t* faces) {
+  NRT_REQUIRE(result, "mc_result_copy arguments");
+  mc_copy(result, vertices, reinterpret_cast<unsigned long long*>(faces));
+  return NRT_OK;
+}
+
+void nrt_mc_result_free(void* result) {
+  if (result) mc_release(result);
 }
 
 int nrt_goal_aggregate(const float* uncert_vol, const float* sdf_vol, const int32_t* dims, const float* goal_pts, int64_t n_goal,
