@@ -1,8 +1,10 @@
 #!/usr/bin/env python
-"""Timing of the two "next" rows built around the hot path, at the reference's sizes:
+"""Timing of the "next" rows built around the hot path, at the reference's sizes:
   * ERPDepth2Dist: 1024 x 2048 panorama, 512-texel skybox (src/simulator/habitat_simulator.py:63,143);
   * goal-space uncertainty aggregation: office0 volumes 49 x 56 x 35, goal space 25 x 28 x 3, k = 300 targets
     (configs/default.py:93-96, src/planner/naruto_planner.py:596-735).
+  * marching cubes: the 5 cm office0 lattice 97 x 111 x 69 (configs/default.py:152 save_mesh_voxel_size), SDF of a room;
+    beside it the reference's own extractor compiled where it lies (oracle/_ref), one host core.
 Device time by CUDA events (median of 20 after 5 warm-ups); beside it the torch-op restatement of the reference (the oracle)
 on the host cores, one call each.  Prints one JSON line."""
 import json
@@ -19,6 +21,8 @@ from naruto_b200.planner_handoff import GoalSpace                 # noqa: E402
 from oracle.erp_oracle import erp_depth2dist                      # noqa: E402  (cpu baseline leg)
 from oracle.planner_oracle import goal_aggregate                  # noqa: E402
 from oracle.make_golden_planner import synth_volumes              # noqa: E402
+from oracle import mc_ref                                         # noqa: E402
+from naruto_b200.marching_cubes import marching_cubes             # noqa: E402
 
 
 def dev_ms(fn, reps=20, warm=5):
@@ -67,6 +71,28 @@ def main():
     out['goal_aggregate'] = {'dims': list(dims), 'goal_points': int(gs.goal_space_pts.shape[0]), 'targets': int(topk.shape[0]),
                              'device_ms': round(ms, 4), 'oracle_cpu_ms': round(cpu_ms, 1),
                              'valid_pairs': int((coll != 0).sum()), 'collections_equal_oracle': bool(torch.equal(res['gs_uncert_collections'].cpu(), coll))}
+    # ---- marching cubes ----
+    import numpy as np
+    nx, ny, nz = 97, 111, 69
+    x, y, z = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing='ij')
+    d = np.stack([x - 3.3, nx - 4.6 - x, y - 2.7, ny - 3.9 - y, z - 2.2, nz - 3.4 - z]).min(0)
+    d = np.minimum(d, np.sqrt((x - 40.2) ** 2 + (y - 61.7) ** 2) - 6.8)
+    vol = np.clip(d + 0.02 * np.random.default_rng(0).standard_normal(d.shape), -2.5, 2.5).astype(np.float32)
+    vd = torch.from_numpy(vol).cuda()
+    marching_cubes(vd, 0.0, 3.0)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        v, f = marching_cubes(vd, 0.0, 3.0)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    rec = {'dims': [nx, ny, nz], 'vertices': int(len(v)), 'faces': int(len(f)), 'wall_ms_device_plus_host_merge': round(statistics.median(ts), 2)}
+    if mc_ref.available():
+        t0 = time.perf_counter()
+        v0, f0 = mc_ref.marching_cubes(vol, 0.0, 3.0)
+        rec['reference_cpu_ms_1_core'] = round((time.perf_counter() - t0) * 1e3, 1)
+        rec['equal_to_reference'] = bool(np.array_equal(v, v0) and np.array_equal(f, f0))
+    out['marching_cubes'] = rec
     print(json.dumps(out), flush=True)
 
 
