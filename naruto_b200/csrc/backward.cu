@@ -51,8 +51,11 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const __grid_constan
     }
     // D = sum_s dL/dw_s * w_s
     float D = 0.f;
+    // (samples outside the truncation window have w == 0: they add nothing to D and get no colour / uncertainty gradient,
+    // so their activations are never evaluated -- ~85 % of the samples)
     for (int s = lane; s < S; s += 32) {
       const float w = wbuf[s];
+      if (w == 0.f) continue;
       const float unc = softplusf_(raw[s * 5 + 4]) + 0.01f;
       float dw = g_rgb[0] * sigmoidf_(raw[s * 5]) + g_rgb[1] * sigmoidf_(raw[s * 5 + 1]) + g_rgb[2] * sigmoidf_(raw[s * 5 + 2]) +
                  g_depth * z[s] + g_U * 2.0f * w * unc;
@@ -64,14 +67,25 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const __grid_constan
     for (int s = lane; s < S; s += 32) {
       const float w = wbuf[s];
       const float sdf = raw[s * 5 + 3], ur = raw[s * 5 + 4], zz = z[s];
-      const float unc = softplusf_(ur) + 0.01f;
-      float c[3], g[5];
+      float g[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      float dw = 0.f;
+      if (w != 0.f) {
+        const float unc = softplusf_(ur) + 0.01f;
+        float c[3];
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        c[k] = sigmoidf_(raw[s * 5 + k]);
-        g[k] = g_rgb[k] * w * c[k] * (1.0f - c[k]);
+        for (int k = 0; k < 3; ++k) {
+          c[k] = sigmoidf_(raw[s * 5 + k]);
+          g[k] = g_rgb[k] * w * c[k] * (1.0f - c[k]);
+        }
+        dw = g_rgb[0] * c[0] + g_rgb[1] * c[1] + g_rgb[2] * c[2] + g_depth * zz + g_U * 2.0f * w * unc;
+        g[4] = g_U * w * w * (ur > 20.0f ? 1.0f : sigmoidf_(ur));
+      } else {
+        // w == 0 but inside the window (bell weight underflowed): dL/dw still flows through the normalisation
+        dw = g_depth * zz;
+        if (zz < ro.z_cut) {
+          dw += g_rgb[0] * sigmoidf_(raw[s * 5]) + g_rgb[1] * sigmoidf_(raw[s * 5 + 1]) + g_rgb[2] * sigmoidf_(raw[s * 5 + 2]);
+        }
       }
-      float dw = g_rgb[0] * c[0] + g_rgb[1] * c[1] + g_rgb[2] * c[2] + g_depth * zz + g_U * 2.0f * w * unc;
       float gs = 0.f;
       if (zz < ro.z_cut) {
         // w = b*m/(T+eps): dL/db = (dL/dw - D)/(T+eps);  b = sig(a)sig(-a), a = sdf/trunc: db/dsdf = b(1-2 sig(a))/trunc
@@ -86,7 +100,6 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const __grid_constan
         gs += g_sdfl * sdf_w * 2.0f * (__fadd_rn(zz, __fmul_rn(sdf, tr)) - td) * tr / NS;
       }
       g[3] = gs;
-      g[4] = g_U * w * w * (ur > 20.0f ? 1.0f : sigmoidf_(ur));
       float* o = draw + (ray * S + s) * 5;
 #pragma unroll
       for (int k = 0; k < 5; ++k) o[k] = g[k];
