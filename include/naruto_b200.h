@@ -181,10 +181,13 @@ int nrt_render_fwd(const NrtPlan* plan, const NrtParams* params, const float* ra
  * src/slam/coslam/model/scene_rep.py:227-287 = render_rays + the loss sums of tp/model/utils.py:81-148): the
  * compositing warps accumulate the shard's loss statistics while the ray's samples are still on chip.  `stats` is the
  * buffer of nrt_loss_partial (nrt_loss_stats_bytes() bytes, zero-filled once at allocation) and receives the same
- * NRT_N_STATS sums; out must provide rgb, depth, uncert, z_vals, raw (and feat for nrt_render_bwd). */
+ * NRT_N_STATS sums; out must provide rgb, depth, uncert, z_vals, raw (and feat for nrt_render_bwd).  With u == NULL the
+ * stratified jitter (torch.rand(z_vals.shape), src/slam/coslam/model/scene_rep.py:176-180) is drawn in the kernel from
+ * Philox keyed by seed; seed_step (optional, dev int32) is mixed into the key at launch, so a replayed CUDA graph draws new
+ * jitter every iteration (pass the step counter advanced by nrt_step_begin). */
 int nrt_render_fwd_stats(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
                          const float* target_rgb, const float* target_d, int64_t n_rays, const float* u, int perturb,
-                         uint64_t seed, const NrtRenderOut* out, double* stats, void* stream);
+                         uint64_t seed, const int32_t* seed_step, const NrtRenderOut* out, double* stats, void* stream);
 
 /* raw2outputs + sdf2weights on caller-provided samples (JointEncodingNaruto.raw2outputs,
  * src/slam/coslam/model/scene_rep.py:66-96): raw dev [B,n_samples,5], z dev [B,n_samples]; fills the per-ray
@@ -237,6 +240,9 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   const int32_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int zero_grad, void* stream);
 int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream);
+/* nrt_counter_add plus the six uniforms of the smoothness lattice (torch.rand(3), torch.rand((1,1,1,3)),
+ * tp/coslam.py:252-258) from Philox keyed by (seed, new counter value) -> rand6_dev (dev fp32 [6], optional). */
+int nrt_step_begin(int32_t* counter_dev, int32_t delta, uint64_t seed, float* rand6_dev, void* stream);
 
 /* ---- device-resident ray sampling ----------------------------------------------------------------
  * The host half of the mapping iteration on device-resident data.  Index lists are dev int64

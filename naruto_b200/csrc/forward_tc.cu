@@ -190,11 +190,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(const __gr
                                                                       const float* __restrict__ rays_d,
                                                                       const float* __restrict__ target_d, int64_t n_rays,
                                                                       const float* __restrict__ z_in, const float* __restrict__ u,
-                                                                      int perturb, uint64_t seed, int rpu, const NrtRenderOut out) {
+                                                                      int perturb, uint64_t seed, const int* __restrict__ seed_step, int rpu,
+                                                                      const NrtRenderOut out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* rest;
   TileCtx c = cta_prologue<TC_COLS>(smem_raw, prm, &rest);
   cta_prologue_finish(smem_raw, c);
+  if (seed_step) seed ^= (uint64_t)(uint32_t)__ldg(seed_step) * 0x9E3779B97F4A7C15ull;
   const int S = P.S;
   float* s_ray = rest;
   float* s_z = s_ray + rpu * 6;
@@ -335,13 +337,13 @@ int launch_map_volumes(const NrtPlan* plan, const NrtParams* prm, const int* dim
 }
 
 int launch_render_fwd_ws(const NrtPlan*, const NrtParams*, const float*, const float*, const float*, int64_t, const float*,
-                         const float*, int, uint64_t, const NrtRenderOut*, const float*, double*, cudaStream_t);   // forward_ws.cu
+                         const float*, int, uint64_t, const NrtRenderOut*, const float*, double*, const int*, cudaStream_t);   // forward_ws.cu
 int launch_loss_partial(const NrtPlan*, const NrtRenderOut*, const float*, const float*, int64_t, double*, cudaStream_t);
 
 // target_rgb / stats non-NULL: also produce the loss statistics of the shard (nrt_render_fwd_stats)
 int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d,
                       const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
-                      const NrtRenderOut* out, const float* target_rgb, double* stats, cudaStream_t st) {
+                      const NrtRenderOut* out, const float* target_rgb, double* stats, const int* seed_step, cudaStream_t st) {
   if (n_rays == 0) return NRT_OK;
   // The warp-specialised kernel (forward_ws.cu) is the product path; NRT_RENDER_IMPL=tc selects the one-role kernel below
   // (same arithmetic, bit-identical results) for A/B measurements.
@@ -350,9 +352,9 @@ int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* ra
     const char* e = getenv("NRT_RENDER_IMPL");
     use_ws = (e && e[0] == 't' && e[1] == 'c' && e[2] == 0) ? 0 : 1;
   }
-  if (use_ws) return launch_render_fwd_ws(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, target_rgb, stats, st);
+  if (use_ws) return launch_render_fwd_ws(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, target_rgb, stats, seed_step, st);
   if (target_rgb) {
-    if (int rc = launch_render_fwd(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, nullptr, nullptr, st)) return rc;
+    if (int rc = launch_render_fwd(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, nullptr, nullptr, seed_step, st)) return rc;
     return launch_loss_partial(plan, out, target_rgb, target_d, n_rays, stats, st);
   }
   const int S = plan->dev.S;
@@ -375,7 +377,7 @@ int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* ra
   }
   const int blocks = (int)(units < slots ? units : slots);
   render_fwd_tc_kernel<<<blocks, TC_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed,
-                                                  (int)rpu, *out);
+                                                  seed_step, (int)rpu, *out);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

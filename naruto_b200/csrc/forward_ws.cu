@@ -82,13 +82,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
                                                                       const float* __restrict__ rays_d,
                                                                       const float* __restrict__ target_d, int64_t n_rays,
                                                                       const float* __restrict__ z_in, const float* __restrict__ u,
-                                                                      int perturb, uint64_t seed, int rpu, const NrtRenderOut out,
-                                                                      const LossFuse lf) {
+                                                                      int perturb, uint64_t seed, const int* __restrict__ seed_step, int rpu,
+                                                                      const NrtRenderOut out, const LossFuse lf) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);           // [2] MMA-complete mbarriers, one per MLP group
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
   float* sw = reinterpret_cast<float*>(smem_raw + TC_SMEM_HEADER);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (seed_step) seed ^= (uint64_t)(uint32_t)__ldg(seed_step) * 0x9E3779B97F4A7C15ull;     // per-iteration jitter under graph replay
   if (warp == 0) {
     if (threadIdx.x == 0) {
       mbar_init(&bars[0], 1);
@@ -363,7 +364,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
 
 int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d,
                          const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
-                         const NrtRenderOut* out, const float* target_rgb, double* stats, cudaStream_t st) {
+                         const NrtRenderOut* out, const float* target_rgb, double* stats, const int* seed_step,
+                         cudaStream_t st) {
   if (n_rays == 0) return NRT_OK;
   const int S = plan->dev.S;
   LossFuse lf{};
@@ -392,7 +394,7 @@ int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float*
   const int64_t want = (units + 1) / 2;
   const int blocks = (int)(want < plan->sm_count ? want : plan->sm_count);
   render_fwd_ws_kernel<<<blocks, WS_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed,
-                                                        (int)rpu, *out, lf);
+                                                        seed_step, (int)rpu, *out, lf);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

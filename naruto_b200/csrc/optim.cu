@@ -165,6 +165,32 @@ int launch_adam(float* p, float* g, float* m, float* v, int64_t n, int step, con
   return NRT_OK;
 }
 
+// Start of a mapping iteration inside a replayed CUDA graph: advance the device-side step counter and draw the six uniforms
+// of the smoothness lattice (torch.rand(3), torch.rand((1,1,1,3)) in tp/coslam.py:252-258) from Philox keyed by (seed, step),
+// so no host value and no separate RNG launch is needed per iteration.
+__global__ void step_begin_kernel(int* c, int delta, uint64_t seed, float* __restrict__ rand6) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int step = *c + delta;
+  *c = step;
+  if (rand6) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint4 a = philox4x32(make_uint4((uint32_t)step, 0x534d4f4fu, 0u, 0u), key);
+    const uint4 b = philox4x32(make_uint4((uint32_t)step, 0x534d4f4fu, 1u, 0u), key);
+    rand6[0] = u32_to_unit(a.x);
+    rand6[1] = u32_to_unit(a.y);
+    rand6[2] = u32_to_unit(a.z);
+    rand6[3] = u32_to_unit(a.w);
+    rand6[4] = u32_to_unit(b.x);
+    rand6[5] = u32_to_unit(b.y);
+  }
+}
+
+int launch_step_begin(int* c, int delta, uint64_t seed, float* rand6, cudaStream_t st) {
+  step_begin_kernel<<<1, 32, 0, st>>>(c, delta, seed, rand6);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
+
 int launch_counter_add(int* c, int delta, cudaStream_t st) {
   counter_add_kernel<<<1, 32, 0, st>>>(c, delta);
   NRT_CUDA_CHECK(cudaGetLastError());

@@ -214,14 +214,15 @@ class FieldPlan:
         return out
 
     def render_fwd_stats(self, P: FieldTensors, rays_o, rays_d, target_rgb, target_d, out: RenderBuffers, stats, u=None,
-                         perturb=None, seed=0):
+                         perturb=None, seed=0, seed_step=None):
         """render_fwd + loss_partial in one launch (training path)."""
         rays_o, rays_d = _f32c(rays_o), _f32c(rays_d)
         perturb = self.perturb if perturb is None else int(perturb)
         cp, cs = P.c_params(), out.c_struct()
         L.check(self.lib.nrt_render_fwd_stats(self.h, C.byref(cp), L.ptr(rays_o), L.ptr(rays_d), L.ptr(_f32c(target_rgb)),
                                               L.ptr(_f32c(target_d).reshape(-1)), rays_o.shape[0],
-                                              L.ptr(_f32c(u)) if u is not None else None, perturb, seed, C.byref(cs),
+                                              L.ptr(_f32c(u)) if u is not None else None, perturb, seed,
+                                              L.ptr(seed_step) if seed_step is not None else None, C.byref(cs),
                                               L.ptr(stats), _stream()))
         return out
 
@@ -259,6 +260,9 @@ class FieldPlan:
     def adam_step(self, p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, zero_grad=False, step_dev=None):
         L.check(self.lib.nrt_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), int(step), L.ptr(step_dev), lr, beta1,
                                        beta2, eps, weight_decay, int(zero_grad), _stream()))
+
+    def step_begin(self, counter, seed=0, rand6=None, delta=1):
+        L.check(self.lib.nrt_step_begin(L.ptr(counter), int(delta), int(seed), L.ptr(rand6) if rand6 is not None else None, _stream()))
 
     def counter_add(self, counter, delta=1):
         L.check(self.lib.nrt_counter_add(L.ptr(counter), int(delta), _stream()))

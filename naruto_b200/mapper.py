@@ -71,6 +71,7 @@ class MappingStep:
         self.it = 0
         self.use_graph = use_graph
         self.external_random = False     # test hook: keep caller-written self.u / self.rand6 instead of drawing
+        self.seed = 0x9E3779B9 + 7919 * self.rank          # per-rank jitter stream (RNG must be rank-offset)
         self._graphs = {}
         self.launches_per_iter = {False: 0, True: 0}
 
@@ -78,12 +79,15 @@ class MappingStep:
     def _body(self, with_uncert_step: bool):
         """The launches of one iteration on the current stream.  Returns how many kernels of ours it launched."""
         p, n = self.plan, 0
-        if not self.external_random:
-            self.u.uniform_()                               # the reference's torch.rand(z_vals.shape) draw
-            if self.smooth_on:
-                self.rand6.uniform_()                       # torch.rand(3), torch.rand((1,1,1,3))
-        p.counter_add(self.map_step, 1); n += 1
-        p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=self.u); n += 1
+        if self.external_random:                            # test hook: caller-written self.u / self.rand6 (the reference's draws)
+            p.counter_add(self.map_step, 1); n += 1
+            p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=self.u); n += 1
+        else:
+            # the reference's torch.rand(z_vals.shape), torch.rand(3), torch.rand((1,1,1,3)) draws, made on the device from Philox
+            # keyed by (seed, step counter): nothing host-side changes between graph replays
+            p.step_begin(self.map_step, self.seed, self.rand6 if self.smooth_on else None); n += 1
+            p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=None,
+                               seed=self.seed, seed_step=self.map_step); n += 1
         reduce_stats(self.stats, self.pg)
         p.loss_finalize(self.stats, self.losses); n += 1
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,

@@ -59,6 +59,37 @@ def test_mapping_iterations_match_oracle(use_graph):
     assert ms.launches_per_iter[False] == 9 and ms.launches_per_iter[True] == 11
 
 
+@pytest.mark.parametrize('use_graph', [False, True])
+def test_device_side_random_draws_change_every_iteration(use_graph):
+    """Production mode (no caller-provided draws): the stratified jitter and the smoothness-lattice offsets come from Philox
+    keyed by (seed, device step counter), so a REPLAYED graph still draws new values each iteration; depths stay sorted and
+    inside the strata; two ranks (seeds) draw different jitter."""
+    dev = torch.device('cuda:0')
+    sp, P, ms = _setup(dev, 64, 32, 5, use_graph)
+    ms.external_random = False
+    o, d, rgb, td = synth_rays(sp, 64, seed=77)
+    zs, r6 = [], []
+    for it in range(4):
+        losses = ms.step(o.to(dev), d.to(dev), rgb.to(dev), td.to(dev))
+        torch.cuda.synchronize()
+        assert torch.isfinite(losses[:5]).all()
+        z = ms.out.z_vals.clone()
+        assert (z[:, 1:] >= z[:, :-1]).all()
+        zs.append(z)
+        r6.append(ms.rand6.clone())
+        assert (ms.rand6 >= 0).all() and (ms.rand6 < 1).all()
+    for a in range(4):
+        for b in range(a + 1, 4):
+            assert (zs[a] != zs[b]).float().mean() > 0.9, 'jitter must change between iterations'
+            assert not torch.equal(r6[a], r6[b])
+    # jitter is uniform inside each stratum: the mean offset from the unperturbed depths is ~0 over many samples
+    ms.seed += 7919                                   # what another rank would use
+    ms._graphs.clear()
+    ms.step(o.to(dev), d.to(dev), rgb.to(dev), td.to(dev))
+    torch.cuda.synchronize()
+    assert (ms.out.z_vals != zs[-1]).float().mean() > 0.9
+
+
 def test_smoothness_vs_oracle():
     dev = torch.device('cuda:0')
     sp, P, ms = _setup(dev, 8, 32, 43, False)
