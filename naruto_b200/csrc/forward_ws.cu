@@ -36,8 +36,10 @@
 
 // Optional fused loss statistics (what nrt_loss_partial computes from the materialised outputs; forward.cu:
 // loss_partial_kernel): the compositing warp already holds the ray's z / raw in shared memory and its integrals in
-// registers.  Per-warp fp64 partial sums live in shared memory, are folded per CTA at the end and reduced in CTA order by the
-// last CTA to finish, so the result does not depend on scheduling.
+// registers.  Lane k of every warp keeps the fp64 partial sum of statistic k in a register (no shared memory while the kernel
+// runs: the shared-memory footprint decides the L1 carve-out, and 2 KB more cost the forward 3-6 %); the partials are folded
+// per CTA at the end through the then idle ring area and reduced in CTA order by the last CTA to finish, so the result does
+// not depend on scheduling.
 struct LossFuse {
   const float* target_rgb;   // NULL: statistics off
   const float* target_d;
@@ -77,6 +79,9 @@ __device__ __forceinline__ void ws_point(const DevPlan& P, const float* __restri
   }
 }
 
+// TRAIN: the launch saves what the backward pass needs (hash features, ReLU masks) and / or accumulates the loss statistics.
+// Forward-only launches (evaluation, the uncertainty sweep) run the instantiation without any of that code.
+template <bool TRAIN>
 __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
                                                                       const float* __restrict__ rays_o,
                                                                       const float* __restrict__ rays_d,
@@ -117,9 +122,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
   float* s_z = s_ray + rpu * 6;
   float* s_raw = s_z + rpu * S;
   const float2* grid = reinterpret_cast<const float2*>(prm.grid);
-  double* s_stat = reinterpret_cast<double*>(sw + 2 * FW_FLOATS + 2 * (WS_NST * WS_STAGE_FLOATS) + 2 * (rpu * (6 + 6 * S))) +
-                   warp * WS_STAT_SLOTS;                              // this warp's partial sums
-  if (lf.target_rgb && lane < WS_STAT_SLOTS) s_stat[lane] = lane == NRT_STAT_UNCERT_MIN ? 3.4e38 : 0.0;
+  double st_acc = lane == NRT_STAT_UNCERT_MIN ? 3.4e38 : 0.0;      // lane k: partial sum of loss statistic k (LossFuse)
 
   TileCtx c;
   c.tb = tmem_base + 256u * (uint32_t)g;
@@ -199,9 +202,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
           tmem_ld16(c.lane_tb + TC_ACC + 16 * q, h);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            h[j] = fmaxf(h[j], 0.f);
-            if (h[j] > 0.f) m1 |= 1u << (16 * q + j);
+          for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+          if (TRAIN && out.masks) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m1 |= (h[j] > 0.f ? 1u : 0u) << (16 * q + j);
           }
           stage16(c, TA_X0 + 16 * q, h);
         }
@@ -215,13 +219,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
           tmem_ld16(c.lane_tb + TC_ACC + 16 + 16 * q, h);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            h[j] = fmaxf(h[j], 0.f);
-            if (h[j] > 0.f) m3 |= 1u << (16 * q + j);
+          for (int j = 0; j < 16; ++j) h[j] = fmaxf(h[j], 0.f);
+          if (TRAIN && out.masks) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) m3 |= (h[j] > 0.f ? 1u : 0u) << (16 * q + j);
           }
           stage16(c, TA_X0 + 16 * q, h);
         }
-        if (out.masks && pl < npts) reinterpret_cast<uint2*>(out.masks)[r0 * S + pl] = make_uint2(m1, m3);
+        if (TRAIN && out.masks && pl < npts) reinterpret_cast<uint2*>(out.masks)[r0 * S + pl] = make_uint2(m1, m3);
         // ---- phase 3: rgb logits = W4 relu(a3) ----
         ws_run_layer<32, 16>(c, g, issuer, TA_X0, c.w_hi + FW_W4 * 4, c.w_lo + FW_W4 * 4);
         float r4[4];
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
         const int pl = t0 + row;
         float x0, x1, x2;
         ws_point(P, s_ray, s_z, pl, npts, S, x0, x1, x2);
-        float* feat_row = (out.feat && pl < npts) ? out.feat + (r0 * S + pl) * NRT_ENC : nullptr;
+        float* feat_row = (TRAIN && out.feat && pl < npts) ? out.feat + (r0 * S + pl) * NRT_ENC : nullptr;
         if (cnt >= WS_NST) bar_sync(WS_BAR_EMPTY(g, st), WS_SUB);
         float4* sf = reinterpret_cast<float4*>(ring + st * WS_STAGE_FLOATS);
 #pragma unroll 1
@@ -283,7 +288,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
         for (int s = lane; s < S; s += 32) out.z_vals[ray * S + s] = z[s];
       if (out.raw)
         for (int i = lane; i < S * 5; i += 32) out.raw[ray * S * 5 + i] = raw[i];
-      if (lf.target_rgb) {
+      if (TRAIN && lf.target_rgb) {
         // per-sample masks: front = z < d - tr ; back = z > d + tr ; sdf_mask = !front & !back & (d > 0)   (tp/model/utils.py:81-148)
         const float td = __ldg(lf.target_d + ray);
         const float tr = P.sc_trunc;
@@ -305,24 +310,28 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
         fsq = warp_sum(fsq);
         nsd = warp_sum(nsd);
         ssq = warp_sum(ssq);
-        if (lane == 0) {
+        {
           const float e0 = ro.rgb[0] - __ldg(lf.target_rgb + ray * 3 + 0), e1 = ro.rgb[1] - __ldg(lf.target_rgb + ray * 3 + 1),
                       e2 = ro.rgb[2] - __ldg(lf.target_rgb + ray * 3 + 2);
-          s_stat[NRT_STAT_N_RAYS] += 1.0;
-          s_stat[NRT_STAT_RGB_SQ] += (double)(e0 * e0) + (double)(e1 * e1) + (double)(e2 * e2);
-          s_stat[NRT_STAT_UNCERT_MIN] = fmin(s_stat[NRT_STAT_UNCERT_MIN], (double)ro.uncert);
-          if (td > 0.0f && td < P.depth_trunc) {
-            const float e = ro.depth - td;
-            s_stat[NRT_STAT_N_VALID] += 1.0;
-            s_stat[NRT_STAT_DEPTH_SQ] += (double)(e * e);
-            s_stat[NRT_STAT_INV2U] += (double)(1.0f / (2.0f * (ro.uncert + 1e-9f)));
-            s_stat[NRT_STAT_LOGU] += (double)logf(ro.uncert + 1e-9f);
+          const bool valid = td > 0.0f && td < P.depth_trunc;
+          const float ed = ro.depth - td;
+          // every lane holds the ray's values (warp-uniform); lane k adds the one that belongs to statistic k
+          double v = 0.0;
+          switch (lane) {
+            case NRT_STAT_N_RAYS: v = 1.0; break;
+            case NRT_STAT_N_VALID: v = valid ? 1.0 : 0.0; break;
+            case NRT_STAT_N_FS: v = (double)nfs; break;
+            case NRT_STAT_N_SDF: v = (double)nsd; break;
+            case NRT_STAT_N_SAMPLES: v = (double)S; break;
+            case NRT_STAT_RGB_SQ: v = (double)(e0 * e0) + (double)(e1 * e1) + (double)(e2 * e2); break;
+            case NRT_STAT_DEPTH_SQ: v = valid ? (double)(ed * ed) : 0.0; break;
+            case NRT_STAT_FS_SQ: v = (double)fsq; break;
+            case NRT_STAT_SDF_SQ: v = (double)ssq; break;
+            case NRT_STAT_INV2U: v = valid ? (double)(1.0f / (2.0f * (ro.uncert + 1e-9f))) : 0.0; break;
+            case NRT_STAT_LOGU: v = valid ? (double)logf(ro.uncert + 1e-9f) : 0.0; break;
+            default: break;
           }
-          s_stat[NRT_STAT_N_SAMPLES] += (double)S;
-          s_stat[NRT_STAT_N_FS] += (double)nfs;
-          s_stat[NRT_STAT_FS_SQ] += (double)fsq;
-          s_stat[NRT_STAT_N_SDF] += (double)nsd;
-          s_stat[NRT_STAT_SDF_SQ] += (double)ssq;
+          st_acc = lane == NRT_STAT_UNCERT_MIN ? fmin(st_acc, (double)ro.uncert) : st_acc + v;
         }
       }
     }
@@ -331,10 +340,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<WS_COLS>(tmem_base);
-  if (lf.target_rgb) {
+  if (TRAIN && lf.target_rgb) {
     // fold the 24 warps in warp order, publish this CTA's partial, let the last CTA reduce all partials in CTA order
     volatile uint32_t* s_last = reinterpret_cast<volatile uint32_t*>(smem_raw + 32);    // header slack
-    const double* all = s_stat - warp * WS_STAT_SLOTS;
+    double* all = reinterpret_cast<double*>(sw + 2 * FW_FLOATS);                        // the ring area is idle by now
+    if (lane < WS_STAT_SLOTS) all[warp * WS_STAT_SLOTS + lane] = st_acc;
+    __syncthreads();
     if (threadIdx.x < NRT_N_STATS) {
       double v = 0.0;
       if (threadIdx.x < NRT_N_STATS_SUM) {
@@ -384,17 +395,21 @@ int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float*
   if (rpu > cap) rpu = cap;
   if (rpu < 1) rpu = 1;
   const int64_t units = (n_rays + rpu - 1) / rpu;
-  const size_t smem = TC_SMEM_WEIGHTS + (size_t)(2 * WS_NST * WS_STAGE_FLOATS + 2 * rpu * (6 + 6 * S)) * sizeof(float) +
-                      (size_t)(WS_THREADS / 32) * WS_STAT_SLOTS * sizeof(double);
+  const size_t smem = TC_SMEM_WEIGHTS + (size_t)(2 * WS_NST * WS_STAGE_FLOATS + 2 * rpu * (6 + 6 * S)) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const int64_t want = (units + 1) / 2;
   const int blocks = (int)(want < plan->sm_count ? want : plan->sm_count);
-  render_fwd_ws_kernel<<<blocks, WS_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed,
-                                                        seed_step, (int)rpu, *out, lf);
+  if (out->feat || out->masks || target_rgb)
+    render_fwd_ws_kernel<true><<<blocks, WS_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb,
+                                                                seed, seed_step, (int)rpu, *out, lf);
+  else
+    render_fwd_ws_kernel<false><<<blocks, WS_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb,
+                                                                 seed, seed_step, (int)rpu, *out, lf);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }
