@@ -81,6 +81,35 @@ def test_fused_loss_statistics_equal_stand_alone_kernel(n_samples_d, B):
         assert abs(sa[i] - sb[i]) <= 2e-6 * abs(sa[i]) + 1e-12, (i, sa[i], sb[i])
 
 
+def test_one_role_kernel_gives_identical_bits(tmp_path):
+    """NRT_RENDER_IMPL=tc (the one-role thread-pair kernel kept for A/B runs) and the warp-specialised product kernel run the
+    same arithmetic: outputs must be bit-identical.  The switch is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = '''
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from test_scale_properties import _plan, _rays
+from naruto_b200.field import RenderBuffers
+cfg, plan, P = _plan(117)
+o, d, rgb, td = _rays(203, seed=9)
+u = torch.rand(203, plan.S, generator=torch.Generator().manual_seed(1)).cuda()
+out = RenderBuffers(203, plan.S, 'cuda', per_sample=True, weights=True, feat=True)
+plan.render_fwd(P, o, d, td, out, u=u)
+torch.save({k: getattr(out, k).cpu() for k in ('rgb', 'depth', 'uncert', 'z_vals', 'raw', 'weights', 'feat', 'masks')}, sys.argv[1])
+''' % (root, os.path.join(root, 'tests'))
+    res = {}
+    for impl in ('ws', 'tc'):
+        f = str(tmp_path / (impl + '.pt'))
+        env = dict(os.environ, NRT_RENDER_IMPL=impl)
+        subprocess.run([sys.executable, '-c', code, f], check=True, env=env, timeout=300)
+        res[impl] = torch.load(f)
+    for k in res['ws']:
+        assert torch.equal(res['ws'][k], res['tc'][k]), k
+
+
 def test_empty_inputs():
     from naruto_b200.field import RenderBuffers
     cfg, plan, P = _plan(32)
