@@ -227,10 +227,14 @@ int nrt_render_bwd(const NrtPlan* plan, const NrtParams* params, const float* ra
  * border `margin`).  rand6: dev fp32 [6] = the reference's two uniform draws, torch.rand(3) (offset) then
  * torch.rand((1,1,1,3)) (jitter); kept on the device so a captured CUDA graph can be replayed with fresh draws.
  * loss (dev fp32 [1], overwritten) = tv / n^3;  dgrid += loss_scale * d loss / d grid (dgrid may be NULL).
- * workspace: dev scratch of nrt_smooth_workspace(n) bytes. */
+ * workspace: dev scratch of nrt_smooth_workspace(n) bytes.
+ * part / n_parts: the term is independent of the rays, so data-parallel ranks split it: every rank encodes the whole
+ * lattice but forms the loss and scatters the gradient only for slab `part` of `n_parts` of the lattice's scan order; the
+ * slabs add up to the whole term (sum loss and dgrid over ranks, e.g. inside the gradient all-reduce).  0 / 1 = all of it. */
 int64_t nrt_smooth_workspace(const NrtPlan* plan, int32_t n);
 int nrt_smooth_fwd_bwd(const NrtPlan* plan, const float* grid, const float* rand6, int32_t n, double voxel,
-                       double margin, float loss_scale, float* loss, float* dgrid, void* workspace, void* stream);
+                       double margin, float loss_scale, float* loss, float* dgrid, void* workspace, int32_t part,
+                       int32_t n_parts, void* stream);
 
 /* ---- optimiser ------------------------------------------------------------------------------- */
 /* torch.optim.Adam (no amsgrad): grad += weight_decay * p; m, v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).

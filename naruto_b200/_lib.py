@@ -80,7 +80,8 @@ SIGNATURES = {
     'nrt_render_bwd': (C.c_int, [_P, C.POINTER(NrtParams), c_fp, c_fp, c_fp, c_fp, C.c_int64, C.POINTER(NrtRenderOut),
                                  c_fp, c_fp, C.POINTER(NrtGrads), c_fp, _P]),
     'nrt_smooth_workspace': (C.c_int64, [_P, C.c_int32]),
-    'nrt_smooth_fwd_bwd': (C.c_int, [_P, c_fp, c_fp, C.c_int32, C.c_double, C.c_double, c_f, c_fp, c_fp, c_fp, _P]),
+    'nrt_smooth_fwd_bwd': (C.c_int, [_P, c_fp, c_fp, C.c_int32, C.c_double, C.c_double, c_f, c_fp, c_fp, c_fp, C.c_int32, C.c_int32,
+                                     _P]),
     'nrt_adam_step': (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_int32, c_fp, c_f, c_f, c_f, c_f, c_f, C.c_int, _P]),
     'nrt_counter_add': (C.c_int, [c_fp, C.c_int32, _P]),
     'nrt_map_volumes': (C.c_int, [_P, C.POINTER(NrtParams), C.POINTER(C.c_int32), c_fp, c_fp, _P]),

@@ -25,7 +25,7 @@ int launch_decode_bwd(const NrtPlan*, const NrtParams*, const PointSource&, int6
                       const NrtGrads*, cudaStream_t);
 int launch_encode_bwd(const NrtPlan*, const float*, const PointSource&, int64_t, const float*, float, float*, float*,
                       cudaStream_t);
-int launch_smooth(const NrtPlan*, const float*, const float*, int, double, double, float, float*, float*, void*, cudaStream_t);
+int launch_smooth(const NrtPlan*, const float*, const float*, int, double, double, float, float*, float*, void*, int, int, cudaStream_t);
 int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
                 cudaStream_t);
 int launch_counter_add(int*, int, cudaStream_t);
@@ -284,9 +284,10 @@ int64_t nrt_smooth_workspace(const NrtPlan* plan, int32_t n) {
 }
 
 int nrt_smooth_fwd_bwd(const NrtPlan* plan, const float* grid, const float* rand6, int32_t n, double voxel, double margin,
-                       float loss_scale, float* loss, float* dgrid, void* workspace, void* stream) {
+                       float loss_scale, float* loss, float* dgrid, void* workspace, int32_t part, int32_t n_parts, void* stream) {
   NRT_REQUIRE(plan && grid && rand6 && loss && workspace && n >= 2, "smooth arguments");
-  return launch_smooth(plan, grid, rand6, n, voxel, margin, loss_scale, loss, dgrid, workspace, (cudaStream_t)stream);
+  NRT_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "smooth: 0 <= part < n_parts");
+  return launch_smooth(plan, grid, rand6, n, voxel, margin, loss_scale, loss, dgrid, workspace, part, n_parts, (cudaStream_t)stream);
 }
 
 int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t step,

@@ -48,16 +48,19 @@ __global__ void __launch_bounds__(256) smooth_encode_kernel(const __grid_constan
 // d/dF[p] of sum over edges (F[p]-F[q])^2 = 2 * sum over neighbours (F[p]-F[q]).
 __global__ void __launch_bounds__(256) smooth_tv_bwd_kernel(const __grid_constant__ DevPlan P, const float* __restrict__ rnd,
                                                             const LatticeSpec ls, const float2* __restrict__ F,
-                                                            float loss_scale, float* __restrict__ loss, float2* __restrict__ dgrid) {
+                                                            float loss_scale, float* __restrict__ loss, float2* __restrict__ dgrid,
+                                                            int64_t pt_lo, int64_t pt_hi) {
   __shared__ float s_red[8];
   const int l = blockIdx.y;
   const int n = ls.n;
   const int m = n - 1;
   const int64_t total = (int64_t)m * m * m;
-  const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // this launch owns the lattice points [pt_lo, pt_hi) of the scan order (all of them on one GPU; a slab per rank otherwise:
+  // every edge is counted at its lower end and every gradient belongs to one point, so the slabs add up to the whole term)
+  const int64_t pt = pt_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float2* __restrict__ Fl = F + (int64_t)l * total;
   float tv = 0.f;
-  if (pt < total) {
+  if (pt < pt_hi) {
     const int idx[3] = {(int)(pt / ((int64_t)m * m)), (int)((pt / m) % m), (int)(pt % m)};
     const int64_t stride[3] = {(int64_t)m * m, m, 1};
     const float2 f = Fl[pt];
@@ -105,16 +108,20 @@ __global__ void __launch_bounds__(256) smooth_tv_bwd_kernel(const __grid_constan
 }
 
 int launch_smooth(const NrtPlan* plan, const float* grid, const float* rnd6, int n, double voxel, double margin,
-                  float loss_scale, float* loss, float* dgrid, void* workspace, cudaStream_t st) {
+                  float loss_scale, float* loss, float* dgrid, void* workspace, int part, int n_parts, cudaStream_t st) {
   const int m = n - 1;
   const int64_t pts = (int64_t)m * m * m;
   const dim3 blocks((unsigned)((pts + 255) / 256), NRT_L);
+  const int64_t lo = pts * part / n_parts, hi = pts * (part + 1) / n_parts;      // this part's slab of the scan order
   float2* F = reinterpret_cast<float2*>(workspace);
   LatticeSpec ls{n, (float)voxel, (float)((double)(n - 1) * voxel), (float)margin, (float)(2.0 * margin)};
   NRT_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), st));
   smooth_encode_kernel<<<blocks, 256, 0, st>>>(plan->dev, (const float2*)grid, rnd6, ls, F);
   NRT_CUDA_CHECK(cudaGetLastError());
-  smooth_tv_bwd_kernel<<<blocks, 256, 0, st>>>(plan->dev, rnd6, ls, F, loss_scale, loss, (float2*)dgrid);
+  if (hi > lo) {
+    const dim3 tv_blocks((unsigned)((hi - lo + 255) / 256), NRT_L);
+    smooth_tv_bwd_kernel<<<tv_blocks, 256, 0, st>>>(plan->dev, rnd6, ls, F, loss_scale, loss, (float2*)dgrid, lo, hi);
+  }
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

@@ -253,9 +253,10 @@ class FieldPlan:
     def smooth_workspace(self, n, device):
         return torch.empty(self.lib.nrt_smooth_workspace(self.h, n) // 4, dtype=torch.float32, device=device)
 
-    def smooth_fwd_bwd(self, grid, rand6, n, voxel, margin, loss_scale, loss_out, dgrid, workspace):
+    def smooth_fwd_bwd(self, grid, rand6, n, voxel, margin, loss_scale, loss_out, dgrid, workspace, part=0, n_parts=1):
         L.check(self.lib.nrt_smooth_fwd_bwd(self.h, L.ptr(_f32c(grid)), L.ptr(rand6), int(n), float(voxel), float(margin),
-                                            float(loss_scale), L.ptr(loss_out), L.ptr(dgrid), L.ptr(workspace), _stream()))
+                                            float(loss_scale), L.ptr(loss_out), L.ptr(dgrid), L.ptr(workspace), int(part),
+                                            int(n_parts), _stream()))
 
     def adam_step(self, p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, zero_grad=False, step_dev=None):
         L.check(self.lib.nrt_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), int(step), L.ptr(step_dev), lr, beta1,

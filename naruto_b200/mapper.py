@@ -33,7 +33,10 @@ class MappingStep:
         self.n_grid, self.n_dec, self.n_unc = sizes[0], sum(sizes[1:5]), sizes[5]
         total = sum(sizes)
         self.theta = torch.zeros(total, **f32)          # parameters, one flat buffer
-        self.grad = torch.zeros(total, **f32)           # gradients, same layout (the all-reduce bucket)
+        # gradients, same layout, plus one trailing slot for this rank's part of the smoothness loss: the whole buffer is the
+        # all-reduce bucket, so the loss value is summed across ranks for free
+        self.bucket = torch.zeros(total + 1, **f32)
+        self.grad = self.bucket[:total]
         self.exp_avg = torch.zeros(total, **f32)
         self.exp_avg_sq = torch.zeros(total, **f32)
 
@@ -61,7 +64,7 @@ class MappingStep:
         self.rand6 = torch.zeros(6, **f32)
         self.stats = plan.new_stats(self.dev)
         self.losses = torch.zeros(L.N_LOSS, **f32)
-        self.smooth_loss = torch.zeros(1, **f32)
+        self.smooth_loss = self.bucket[total:total + 1]
         self.loss_grad = torch.tensor([t['rgb_weight'], t['depth_weight'], t['sdf_weight'], t['fs_weight'],
                                        t.get('uncert_weight', 0.0)], **f32)
         self.ws_bwd = torch.empty(plan.lib.nrt_render_bwd_workspace(plan.h, self.B) // 4, **f32)
@@ -92,10 +95,10 @@ class MappingStep:
         p.loss_finalize(self.stats, self.losses); n += 1
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,
                      self.G, workspace=self.ws_bwd); n += 2
-        if self.smooth_on and self.rank == 0:               # ray-independent term: added once, on rank 0
+        if self.smooth_on:                                  # ray-independent term: every rank takes one slab of the lattice
             p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
-                             self.smooth_loss, self.G.grid, self.ws_smooth); n += 2
-        reduce_grads(self.grad, self.pg)
+                             self.smooth_loss, self.G.grid, self.ws_smooth, part=self.rank, n_parts=self.world); n += 2
+        reduce_grads(self.bucket, self.pg)
         ng, nd = self.n_grid, self.n_dec
         # create_optimizer (src/slam/coslam/coslam.py:409-419): decoder group wd=1e-6, grid group eps=1e-15, betas (0.9,0.99)
         p.adam_step(self.theta[:ng], self.grad[:ng], self.exp_avg[:ng], self.exp_avg_sq[:ng], 0, self.lr_embed, 0.9, 0.99,

@@ -107,6 +107,29 @@ def test_smoothness_vs_oracle():
     assert (ga - gb).abs().max() <= 1e-4 * gb.abs().max()
 
 
+def test_smoothness_slabs_add_up_to_the_whole_term():
+    """Data-parallel ranks split the ray-independent smoothness term into slabs of the lattice (part / n_parts): the slabs'
+    losses and gradients must add up to the single-GPU term."""
+    dev = torch.device('cuda:0')
+    sp, P, ms = _setup(dev, 8, 32, 43, False)
+    ms.rand6.copy_(torch.rand(6, generator=torch.Generator().manual_seed(6)))
+    args = (ms.P.grid, ms.rand6, sp.smooth_pts, sp.smooth_vox, sp.smooth_margin, 1.5)
+    ms.grad.zero_()
+    ms.plan.smooth_fwd_bwd(*args, ms.smooth_loss, ms.G.grid, ms.ws_smooth)
+    torch.cuda.synchronize()
+    whole_loss, whole_grad = ms.smooth_loss.item(), ms.G.grid.clone()
+    assert whole_loss > 0 and whole_grad.abs().max() > 0
+    for n_parts in (2, 3, 8):
+        ms.grad.zero_()
+        tot = 0.0
+        for part in range(n_parts):
+            ms.plan.smooth_fwd_bwd(*args, ms.smooth_loss, ms.G.grid, ms.ws_smooth, part=part, n_parts=n_parts)
+            torch.cuda.synchronize()
+            tot += ms.smooth_loss.item()
+        assert abs(tot - whole_loss) <= 1e-5 * whole_loss, (n_parts, tot, whole_loss)
+        assert (ms.G.grid - whole_grad).abs().max() <= 1e-5 * whole_grad.abs().max(), n_parts
+
+
 def test_adam_kernel_vs_torch():
     dev = torch.device('cuda:0')
     from naruto_b200.configs import replica_office0, OFFICE0_BOUND
