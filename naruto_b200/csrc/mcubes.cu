@@ -18,6 +18,7 @@
 //                         O(#triangles), as in the reference.
 // All arithmetic that decides a branch or produces a coordinate is written with explicit round-to-nearest intrinsics in the
 // reference's operation order, so device and reference agree bit for bit.
+#include <memory>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -303,7 +304,7 @@ int mc_extract(const float* vol, int nx, int ny, int nz, float iso, float trunca
   long long* bsum = reinterpret_cast<long long*>(w + ((corners * 4 + cells * 4 + 255) / 256) * 256);
   long long* total_dev = bsum + nb;
   const float thresh = 10.0f;
-  McResult* res = new McResult();
+  std::unique_ptr<McResult> res(new McResult());          // released to the caller only on success
   if (cells > 0) {
     const unsigned g1 = (unsigned)((corners + 255) / 256 < 148 * 16 ? (corners + 255) / 256 : 148 * 16);
     mc_corners_kernel<<<g1, 256, 0, st>>>(vol, nx, ny, nz, truncation, corner);
@@ -323,7 +324,6 @@ int mc_extract(const float* vol, int nx, int ny, int nz, float iso, float trunca
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
       cudaFree(soup_dev);
       if (e != cudaSuccess) {
-        delete res;
         nrt_set_error("marching cubes: %s", cudaGetErrorString(e));
         return NRT_ERR_CUDA;
       }
@@ -331,7 +331,7 @@ int mc_extract(const float* vol, int nx, int ny, int nz, float iso, float trunca
     }
     NRT_CUDA_CHECK(cudaGetLastError());
   }
-  *handle = res;
+  *handle = res.release();
   return NRT_OK;
 }
 
