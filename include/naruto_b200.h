@@ -110,7 +110,8 @@ typedef struct NrtRenderOut {
   float* z_vals;      /* dev [B,S] */
   float* raw;         /* dev [B,S,5] = rgb logits(3), sdf, raw uncertainty */
   float* weights;     /* dev [B,S] */
-  float* feat;        /* dev [B*S,32] hash features, saved for nrt_render_bwd (training) */
+  float* feat;        /* dev, ceil(B*S/128)*128*32 floats: hash features saved for nrt_render_bwd (training), opaque tile-major
+                       * layout [tile of 128 points][8 chunks][128 points][4 floats] (coalesced for writer and reader) */
   uint32_t* masks;    /* dev [B*S,2] ReLU masks of the two hidden layers (bit j = unit j active), saved for nrt_render_bwd:
                        * with them the backward recomputes activations in single-pass TF32 (they only feed the tf32
                        * weight-gradient operands) instead of 3xTF32; optional (NULL: masks are recomputed exactly) */

@@ -21,7 +21,7 @@ int launch_loss_partial(const NrtPlan*, const NrtRenderOut*, const float*, const
 int launch_loss_finalize(const double*, float*, cudaStream_t);
 int launch_composite_bwd(const NrtPlan*, const NrtRenderOut*, const float*, const float*, int64_t, const double*, const float*,
                          float*, cudaStream_t);
-int launch_decode_bwd(const NrtPlan*, const NrtParams*, const PointSource&, int64_t, const float*, const uint32_t*, const float*, float*,
+int launch_decode_bwd(const NrtPlan*, const NrtParams*, const PointSource&, int64_t, const float*, int, const uint32_t*, const float*, float*,
                       const NrtGrads*, cudaStream_t);
 int launch_encode_bwd(const NrtPlan*, const float*, const PointSource&, int64_t, const float*, float, float*, float*,
                       cudaStream_t);
@@ -254,7 +254,7 @@ int nrt_decode_bwd(const NrtPlan* plan, const NrtParams* params, const float* x,
   float* feat = reinterpret_cast<float*>(workspace);          // [n,32] recomputed hash features
   if (int rc = launch_encode_fwd(plan, params->grid, x, n, feat, st)) return rc;
   PointSource src{x, nullptr, nullptr, nullptr, 1};
-  return launch_decode_bwd(plan, params, src, n, feat, nullptr, draw, nullptr, grads, st);   // scatters into grads->grid itself
+  return launch_decode_bwd(plan, params, src, n, feat, 0, nullptr, draw, nullptr, grads, st);   // scatters into grads->grid itself
 }
 
 int64_t nrt_render_bwd_workspace(const NrtPlan* plan, int64_t n_rays) {
@@ -274,7 +274,7 @@ int nrt_render_bwd(const NrtPlan* plan, const NrtParams* params, const float* ra
   float* draw = reinterpret_cast<float*>(workspace);
   if (int rc = launch_composite_bwd(plan, rend, target_rgb, target_d, n_rays, stats, loss_grad, draw, st)) return rc;
   PointSource src{nullptr, rays_o, rays_d, rend->z_vals, plan->dev.S};
-  return launch_decode_bwd(plan, params, src, n_pts, rend->feat, rend->masks, draw, nullptr, grads, st);
+  return launch_decode_bwd(plan, params, src, n_pts, rend->feat, 1, rend->masks, draw, nullptr, grads, st);
 }
 
 int64_t nrt_smooth_workspace(const NrtPlan* plan, int32_t n) {

@@ -138,7 +138,7 @@ __device__ __forceinline__ void scatter_warps(const DevPlan& P, const DevLevel* 
 template <bool SAVED>
 __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __grid_constant__ DevPlan P, const NrtParams prm,
                                                                       const PointSource src, int64_t n_pts,
-                                                                      const float* __restrict__ feat,
+                                                                      const float* __restrict__ feat, int feat_tiled,
                                                                       const uint32_t* __restrict__ masks,
                                                                       const float* __restrict__ draw, float* __restrict__ dfeat,
                                                                       const NrtGrads grads) {
@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) decode_bwd_tc_kernel(const __g
       float f[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 v = active ? __ldg(reinterpret_cast<const float4*>(feat + pt * NRT_ENC) + half * 4 + q) : make_float4(0, 0, 0, 0);
+        const int64_t fi = feat_tiled ? feat_tiled_index(pt, half * 4 + q) : pt * 8 + half * 4 + q;
+        const float4 v = active ? __ldg(reinterpret_cast<const float4*>(feat) + fi) : make_float4(0, 0, 0, 0);
         f[4 * q] = v.x;
         f[4 * q + 1] = v.y;
         f[4 * q + 2] = v.z;
@@ -448,8 +449,9 @@ size_t decode_bwd_tc_smem(bool saved) {
   return TC_SMEM_HEADER + (fw + 2 * BW_FLOATS + 128 + XT_FLOATS + YT_FLOATS + (saved ? 2 : 1) * RING_STAGE_FLOATS) * sizeof(float);
 }
 
+// feat_tiled: feat is NrtRenderOut::feat (tile-major, common.cuh: feat_tiled_index); 0: plain [n,32] (nrt_decode_bwd's scratch)
 int launch_decode_bwd(const NrtPlan* plan, const NrtParams* prm, const PointSource& src, int64_t n_pts, const float* feat,
-                      const uint32_t* masks, const float* draw, float* dfeat, const NrtGrads* grads, cudaStream_t st) {
+                      int feat_tiled, const uint32_t* masks, const float* draw, float* dfeat, const NrtGrads* grads, cudaStream_t st) {
   if (n_pts == 0) return NRT_OK;
   const bool saved = masks != nullptr;
   const size_t smem = decode_bwd_tc_smem(saved);
@@ -462,9 +464,9 @@ int launch_decode_bwd(const NrtPlan* plan, const NrtParams* prm, const PointSour
   const int64_t tiles = (n_pts + 127) / 128;
   const int blocks = (int)(tiles < plan->sm_count ? tiles : plan->sm_count);
   if (saved)
-    decode_bwd_tc_kernel<true><<<blocks, BWD_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, masks, draw, dfeat, *grads);
+    decode_bwd_tc_kernel<true><<<blocks, BWD_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, feat_tiled, masks, draw, dfeat, *grads);
   else
-    decode_bwd_tc_kernel<false><<<blocks, BWD_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, nullptr, draw, dfeat, *grads);
+    decode_bwd_tc_kernel<false><<<blocks, BWD_THREADS, smem, st>>>(plan->dev, *prm, src, n_pts, feat, feat_tiled, nullptr, draw, dfeat, *grads);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

@@ -596,6 +596,12 @@ __device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, 
   return r;
 }
 
+// Saved hash features (NrtRenderOut::feat) are stored tile-major: point p, chunk c (4 floats = the two features of two levels)
+// lives at float4 index ((p / 128) * 8 + c) * 128 + p % 128, i.e. [tile of 128 points][8 chunks][128 points][4 floats].  Both the
+// writers (gather threads: one chunk of 32 consecutive points) and the readers (backward thread pairs: chunks of 32 consecutive
+// points) then touch 512 contiguous bytes per warp instruction instead of 32 scattered 16-byte pieces.
+__device__ __forceinline__ int64_t feat_tiled_index(int64_t p, int chunk) { return ((p >> 7) * 8 + chunk) * 128 + (p & 127); }
+
 // where the points of a launch come from: an explicit [n,3] array, or rays + depths
 struct PointSource {
   const float* x;                 // [n,3] normalised points, or NULL -> rays

@@ -35,7 +35,7 @@
 template <bool COLOR>
 __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const float2* __restrict__ grid,
                                             const float* __restrict__ ug, bool active, float x0, float x1, float x2,
-                                            float* __restrict__ feat_out, PointOut& out,
+                                            float4* __restrict__ feat_out, int64_t feat_pt, PointOut& out,
                                             uint16_t* __restrict__ mask_out = nullptr) {
   const int half = tc_half();
   // ---- encodings -> TMEM ----
@@ -47,7 +47,7 @@ __device__ __forceinline__ void decode_tile(const DevPlan& P, TileCtx& c, const 
     const int l0 = 4 * g + 2 * (gi & 1);
     float f[4];
     gather_levels_paired<2>(P.lv + l0, grid, x0, x1, x2, f);
-    if (feat_out) reinterpret_cast<float4*>(feat_out)[l0 >> 1] = make_float4(f[0], f[1], f[2], f[3]);
+    if (feat_out) feat_out[feat_tiled_index(feat_pt, l0 >> 1)] = make_float4(f[0], f[1], f[2], f[3]);
     stage4(c, TA_X0 + 2 * l0, f);
   }
 #pragma unroll 1
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) points_fwd_tc_kernel(const __gr
       }
     }
     PointOut o;
-    decode_tile<COLOR>(P, c, grid, prm.uncert, active, x0, x1, x2, nullptr, o);
+    decode_tile<COLOR>(P, c, grid, prm.uncert, active, x0, x1, x2, nullptr, 0, o);
     if (active && lat.vol_sdf && half == 0) {
       // get_map_volumes: uncertainty only where the point is just outside the surface
       const float sdf = o.o8[0];
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(const __gr
       }
       PointOut po;
       decode_tile<true>(P, c, grid, prm.uncert, active, x0, x1, x2,
-                        (out.feat && active) ? out.feat + (r0 * S + pl) * NRT_ENC : nullptr, po,
+                        (out.feat && active) ? reinterpret_cast<float4*>(out.feat) : nullptr, r0 * S + pl, po,
                         (out.masks && active) ? reinterpret_cast<uint16_t*>(out.masks) + (r0 * S + pl) * 4 : nullptr);
       if (active) {
         float* r = s_raw + pl * 5;

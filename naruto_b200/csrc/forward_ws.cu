@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
         const int pl = t0 + row;
         float x0, x1, x2;
         ws_point(P, s_ray, s_z, pl, npts, S, x0, x1, x2);
-        float* feat_row = (TRAIN && out.feat && pl < npts) ? out.feat + (r0 * S + pl) * NRT_ENC : nullptr;
+        const bool save_feat = TRAIN && out.feat && pl < npts;
+        const int64_t pglob = r0 * S + pl;                               // flat point index of this row
         if (cnt >= WS_NST) bar_sync(WS_BAR_EMPTY(g, st), WS_SUB);
         float4* sf = reinterpret_cast<float4*>(ring + st * WS_STAGE_FLOATS);
 #pragma unroll 1
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
           gather_levels_paired<2>(P.lv + l0, grid, x0, x1, x2, f);
           const float4 v = make_float4(f[0], f[1], f[2], f[3]);
           sf[(l0 >> 1) * WS_ROWS + row] = v;
-          if (feat_row) reinterpret_cast<float4*>(feat_row)[l0 >> 1] = v;
+          if (save_feat) reinterpret_cast<float4*>(out.feat)[feat_tiled_index(pglob, l0 >> 1)] = v;
         }
         bar_arrive(WS_BAR_FULL(g, st), WS_SUB);
       }

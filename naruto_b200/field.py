@@ -61,8 +61,15 @@ class RenderBuffers:
         self.z_vals = torch.empty(B, S, **f) if per_sample else None
         self.raw = torch.empty(B, S, 5, **f) if per_sample else None
         self.weights = torch.empty(B, S, **f) if weights else None
-        self.feat = torch.empty(B * S, ENC_DIMS, **f) if feat else None
+        # saved hash features, tile-major (see NrtRenderOut::feat): padded to whole tiles of 128 points
+        self.feat = torch.zeros((B * S + 127) // 128 * 128, ENC_DIMS, **f) if feat else None
         self.masks = torch.empty(B * S, 2, dtype=torch.int32, device=device) if feat else None      # ReLU masks, saved with feat
+
+    def feat_rows(self):
+        """The saved hash features as a plain [B*S, 32] tensor (un-tiles NrtRenderOut::feat; diagnostics and tests)."""
+        n = self.B * self.S
+        t = self.feat.view(-1, 8, 128, 4).permute(0, 2, 1, 3).reshape(-1, ENC_DIMS)
+        return t[:n].contiguous()
 
     def c_struct(self):
         return L.NrtRenderOut(L.ptr(self.rgb), L.ptr(self.depth), L.ptr(self.depth_var), L.ptr(self.acc), L.ptr(self.disp),

@@ -44,7 +44,7 @@ def test_ray_kernel_equals_point_kernel_plus_compositor(n_samples_d, B):
     x = ((pts - b[:, 0]) / (b[:, 1] - b[:, 0])).reshape(-1, 3).contiguous()
     raw, _, _ = plan.decode_fwd(P, x, with_color=True)
     assert torch.equal(raw.view(B, S, 5), out.raw), (raw.view(B, S, 5) - out.raw).abs().max()
-    assert torch.equal(plan.encode_fwd(P.grid, x), out.feat)
+    assert torch.equal(plan.encode_fwd(P.grid, x), out.feat_rows())
     comp = plan.composite_fwd(out.raw, z)
     for k in ('rgb', 'depth', 'depth_var', 'acc', 'disp', 'uncert', 'weights'):
         assert torch.equal(getattr(comp, k), getattr(out, k)), k
