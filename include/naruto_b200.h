@@ -185,10 +185,13 @@ int nrt_render_fwd(const NrtPlan* plan, const NrtParams* params, const float* ra
  * NRT_N_STATS sums; out must provide rgb, depth, uncert, z_vals, raw (and feat for nrt_render_bwd).  With u == NULL the
  * stratified jitter (torch.rand(z_vals.shape), src/slam/coslam/model/scene_rep.py:176-180) is drawn in the kernel from
  * Philox keyed by seed; seed_step (optional, dev int32) is mixed into the key at launch, so a replayed CUDA graph draws new
- * jitter every iteration (pass the step counter advanced by nrt_step_begin). */
+ * jitter every iteration (pass the step counter advanced by nrt_step_begin).  losses (optional, dev fp32 [NRT_N_LOSS]):
+ * when the shard is the whole batch (one GPU) the last CTA also writes what nrt_loss_finalize would; a multi-GPU caller
+ * passes NULL, sums stats across ranks and calls nrt_loss_finalize. */
 int nrt_render_fwd_stats(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
                          const float* target_rgb, const float* target_d, int64_t n_rays, const float* u, int perturb,
-                         uint64_t seed, const int32_t* seed_step, const NrtRenderOut* out, double* stats, void* stream);
+                         uint64_t seed, const int32_t* seed_step, const NrtRenderOut* out, double* stats, float* losses,
+                         void* stream);
 
 /* raw2outputs + sdf2weights on caller-provided samples (JointEncodingNaruto.raw2outputs,
  * src/slam/coslam/model/scene_rep.py:66-96): raw dev [B,n_samples,5], z dev [B,n_samples]; fills the per-ray

@@ -61,7 +61,7 @@ SIGNATURES = {
     'nrt_render_fwd': (C.c_int, [_P, C.POINTER(NrtParams), c_fp, c_fp, c_fp, C.c_int64, c_fp, c_fp, C.c_int, C.c_uint64,
                                  C.POINTER(NrtRenderOut), _P]),
     'nrt_render_fwd_stats': (C.c_int, [_P, C.POINTER(NrtParams), c_fp, c_fp, c_fp, c_fp, C.c_int64, c_fp, C.c_int, C.c_uint64,
-                                       c_fp, C.POINTER(NrtRenderOut), c_fp, _P]),
+                                       c_fp, C.POINTER(NrtRenderOut), c_fp, c_fp, _P]),
     'nrt_step_begin': (C.c_int, [c_fp, C.c_int32, C.c_uint64, c_fp, _P]),
     'nrt_mc_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     'nrt_mc_extract': (C.c_int, [c_fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, c_fp, _P, C.POINTER(C.c_void_p)]),

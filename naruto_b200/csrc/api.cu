@@ -14,7 +14,7 @@ int launch_oneblob_bwd(const float*, int64_t, const float*, float*, cudaStream_t
 int launch_decode_fwd(const NrtPlan*, const NrtParams*, const float*, int64_t, int, float*, float*, float*, cudaStream_t);
 int launch_sample_z(const NrtPlan*, const float*, int64_t, const float*, int, uint64_t, float*, cudaStream_t);
 int launch_render_fwd(const NrtPlan*, const NrtParams*, const float*, const float*, const float*, int64_t, const float*,
-                      const float*, int, uint64_t, const NrtRenderOut*, const float*, double*, const int*, cudaStream_t);
+                      const float*, int, uint64_t, const NrtRenderOut*, const float*, double*, float*, const int*, cudaStream_t);
 int launch_composite_fwd(const NrtPlan*, const float*, const float*, int64_t, int, const NrtRenderOut*, cudaStream_t);
 int64_t loss_stats_doubles();
 int launch_loss_partial(const NrtPlan*, const NrtRenderOut*, const float*, const float*, int64_t, double*, cudaStream_t);
@@ -206,18 +206,18 @@ int nrt_render_fwd(const NrtPlan* plan, const NrtParams* params, const float* ra
   NRT_REQUIRE(plan && out && n_rays >= 0 && (n_rays == 0 || (rays_o && rays_d)), "render_fwd arguments");
   NRT_REQUIRE(z_in || target_d || n_rays == 0, "render_fwd needs target_d or z_in");
   if (int rc = check_params(params)) return rc;
-  return launch_render_fwd(plan, params, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, nullptr, nullptr, nullptr,
+  return launch_render_fwd(plan, params, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, nullptr, nullptr, nullptr, nullptr,
                            (cudaStream_t)stream);
 }
 
 int nrt_render_fwd_stats(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
                          const float* target_rgb, const float* target_d, int64_t n_rays, const float* u, int perturb,
-                         uint64_t seed, const int32_t* seed_step, const NrtRenderOut* out, double* stats, void* stream) {
+                         uint64_t seed, const int32_t* seed_step, const NrtRenderOut* out, double* stats, float* losses, void* stream) {
   NRT_REQUIRE(plan && out && rays_o && rays_d && target_rgb && target_d && stats && n_rays > 0, "render_fwd_stats arguments");
   NRT_REQUIRE(out->rgb && out->depth && out->uncert && out->z_vals && out->raw, "loss needs rgb, depth, uncert, z_vals, raw");
   if (int rc = check_params(params)) return rc;
   return launch_render_fwd(plan, params, rays_o, rays_d, target_d, n_rays, nullptr, u, perturb, seed, out, target_rgb, stats,
-                           seed_step, (cudaStream_t)stream);
+                           losses, seed_step, (cudaStream_t)stream);
 }
 
 int nrt_composite_fwd(const NrtPlan* plan, const float* raw, const float* z, int64_t n_rays, int32_t n_samples,

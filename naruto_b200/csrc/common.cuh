@@ -626,6 +626,31 @@ __device__ __forceinline__ void fetch_point(const DevPlan& P, const PointSource&
   }
 }
 
+// losses from the (globally summed) statistics: JointEncodingNaruto.forward's train branch + get_sdf_loss
+// (src/slam/coslam/model/scene_rep.py:244-287; tp/model/utils.py:103-148).  One thread.
+__device__ __forceinline__ void finalize_losses(const double* stats, float* __restrict__ losses) {
+  const double B = stats[NRT_STAT_N_RAYS], V = stats[NRT_STAT_N_VALID], NS = stats[NRT_STAT_N_SAMPLES];
+  const double nfs = stats[NRT_STAT_N_FS], nsdf = stats[NRT_STAT_N_SDF];
+  const double ntot = nfs + nsdf;
+  // the reference evaluates these in fp32 tensors; fp64 here only removes summation-order noise
+  float rgb_loss = (float)(stats[NRT_STAT_RGB_SQ] / (3.0 * B));
+  float depth_loss = (float)(stats[NRT_STAT_DEPTH_SQ] / V);
+  float fs_w = 1.0f - (float)nfs / (float)ntot;
+  float sdf_w = 1.0f - (float)nsdf / (float)ntot;
+  float fs_loss = (float)(stats[NRT_STAT_FS_SQ] / NS) * fs_w;
+  float sdf_loss = (float)(stats[NRT_STAT_SDF_SQ] / NS) * sdf_w;
+  float mean_inv2u = (float)(stats[NRT_STAT_INV2U] / V);
+  float uncert_loss = mean_inv2u * depth_loss + 0.5f * (float)(stats[NRT_STAT_LOGU] / V);
+  losses[NRT_LOSS_RGB] = rgb_loss;
+  losses[NRT_LOSS_DEPTH] = depth_loss;
+  losses[NRT_LOSS_SDF] = sdf_loss;
+  losses[NRT_LOSS_FS] = fs_loss;
+  losses[NRT_LOSS_UNCERT] = uncert_loss;
+  losses[NRT_LOSS_PSNR] = -10.0f * logf(rgb_loss) / logf(10.0f);
+  losses[NRT_LOSS_UNCERT_MIN] = (float)stats[NRT_STAT_UNCERT_MIN];
+  losses[NRT_LOSS_RESERVED] = 0.f;
+}
+
 // error plumbing (api.cu)
 void nrt_set_error(const char* fmt, ...);
 #define NRT_CUDA_CHECK(expr)                                                          \

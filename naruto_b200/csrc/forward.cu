@@ -186,26 +186,7 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(const __grid_constant
 
 __global__ void loss_finalize_kernel(const double* __restrict__ stats, float* __restrict__ losses) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const double B = stats[NRT_STAT_N_RAYS], V = stats[NRT_STAT_N_VALID], NS = stats[NRT_STAT_N_SAMPLES];
-  const double nfs = stats[NRT_STAT_N_FS], nsdf = stats[NRT_STAT_N_SDF];
-  const double ntot = nfs + nsdf;
-  // the reference evaluates these in fp32 tensors; fp64 here only removes summation-order noise
-  float rgb_loss = (float)(stats[NRT_STAT_RGB_SQ] / (3.0 * B));
-  float depth_loss = (float)(stats[NRT_STAT_DEPTH_SQ] / V);
-  float fs_w = 1.0f - (float)nfs / (float)ntot;
-  float sdf_w = 1.0f - (float)nsdf / (float)ntot;
-  float fs_loss = (float)(stats[NRT_STAT_FS_SQ] / NS) * fs_w;
-  float sdf_loss = (float)(stats[NRT_STAT_SDF_SQ] / NS) * sdf_w;
-  float mean_inv2u = (float)(stats[NRT_STAT_INV2U] / V);
-  float uncert_loss = mean_inv2u * depth_loss + 0.5f * (float)(stats[NRT_STAT_LOGU] / V);
-  losses[NRT_LOSS_RGB] = rgb_loss;
-  losses[NRT_LOSS_DEPTH] = depth_loss;
-  losses[NRT_LOSS_SDF] = sdf_loss;
-  losses[NRT_LOSS_FS] = fs_loss;
-  losses[NRT_LOSS_UNCERT] = uncert_loss;
-  losses[NRT_LOSS_PSNR] = -10.0f * logf(rgb_loss) / logf(10.0f);
-  losses[NRT_LOSS_UNCERT_MIN] = (float)stats[NRT_STAT_UNCERT_MIN];
-  losses[NRT_LOSS_RESERVED] = 0.f;
+  finalize_losses(stats, losses);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -337,13 +337,15 @@ int launch_map_volumes(const NrtPlan* plan, const NrtParams* prm, const int* dim
 }
 
 int launch_render_fwd_ws(const NrtPlan*, const NrtParams*, const float*, const float*, const float*, int64_t, const float*,
-                         const float*, int, uint64_t, const NrtRenderOut*, const float*, double*, const int*, cudaStream_t);   // forward_ws.cu
+                         const float*, int, uint64_t, const NrtRenderOut*, const float*, double*, float*, const int*, cudaStream_t);   // forward_ws.cu
 int launch_loss_partial(const NrtPlan*, const NrtRenderOut*, const float*, const float*, int64_t, double*, cudaStream_t);
+int launch_loss_finalize(const double*, float*, cudaStream_t);
 
 // target_rgb / stats non-NULL: also produce the loss statistics of the shard (nrt_render_fwd_stats)
 int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d,
                       const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
-                      const NrtRenderOut* out, const float* target_rgb, double* stats, const int* seed_step, cudaStream_t st) {
+                      const NrtRenderOut* out, const float* target_rgb, double* stats, float* losses, const int* seed_step,
+                      cudaStream_t st) {
   if (n_rays == 0) return NRT_OK;
   // The warp-specialised kernel (forward_ws.cu) is the product path; NRT_RENDER_IMPL=tc selects the one-role kernel below
   // (same arithmetic, bit-identical results) for A/B measurements.
@@ -352,10 +354,11 @@ int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* ra
     const char* e = getenv("NRT_RENDER_IMPL");
     use_ws = (e && e[0] == 't' && e[1] == 'c' && e[2] == 0) ? 0 : 1;
   }
-  if (use_ws) return launch_render_fwd_ws(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, target_rgb, stats, seed_step, st);
+  if (use_ws) return launch_render_fwd_ws(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, target_rgb, stats, losses, seed_step, st);
   if (target_rgb) {
-    if (int rc = launch_render_fwd(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, nullptr, nullptr, seed_step, st)) return rc;
-    return launch_loss_partial(plan, out, target_rgb, target_d, n_rays, stats, st);
+    if (int rc = launch_render_fwd(plan, prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed, out, nullptr, nullptr, nullptr, seed_step, st)) return rc;
+    if (int rc = launch_loss_partial(plan, out, target_rgb, target_d, n_rays, stats, st)) return rc;
+    return losses ? launch_loss_finalize(stats, losses, st) : NRT_OK;
   }
   const int S = plan->dev.S;
   const int slots = 2 * plan->sm_count;

@@ -46,6 +46,7 @@ struct LossFuse {
   double* part;              // [gridDim.x][NRT_N_STATS]
   unsigned int* counter;
   double* stats;             // [NRT_N_STATS]
+  float* losses;             // optional [NRT_N_LOSS]: single-shard callers get the finalized losses from the last CTA
 };
 #define WS_STAT_SLOTS 12     // 11 sums + the minimum of uncert_map
 
@@ -371,12 +372,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
       lf.stats[threadIdx.x] = v;
       if (threadIdx.x == 0) *lf.counter = 0u;   // re-arm for the next launch
     }
+    if (lf.losses) {                            // one shard = the whole batch: the losses follow at once (no extra launch)
+      __syncthreads();
+      if (*s_last && threadIdx.x == 0) {
+        __threadfence();
+        finalize_losses(lf.stats, lf.losses);
+      }
+    }
   }
 }
 
 int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d,
                          const float* target_d, int64_t n_rays, const float* z_in, const float* u, int perturb, uint64_t seed,
-                         const NrtRenderOut* out, const float* target_rgb, double* stats, const int* seed_step,
+                         const NrtRenderOut* out, const float* target_rgb, double* stats, float* losses, const int* seed_step,
                          cudaStream_t st) {
   if (n_rays == 0) return NRT_OK;
   const int S = plan->dev.S;
@@ -387,6 +395,7 @@ int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float*
     lf.stats = stats;
     lf.counter = reinterpret_cast<unsigned int*>(stats + NRT_N_STATS);
     lf.part = stats + NRT_N_STATS + 2;
+    lf.losses = losses;
   }
   const int64_t slots = 2 * (int64_t)plan->sm_count;
   // rays per block: every sub-CTA gets the same number of blocks (rounds), each block as large as the staging buffer allows

@@ -221,7 +221,7 @@ class FieldPlan:
         return out
 
     def render_fwd_stats(self, P: FieldTensors, rays_o, rays_d, target_rgb, target_d, out: RenderBuffers, stats, u=None,
-                         perturb=None, seed=0, seed_step=None):
+                         perturb=None, seed=0, seed_step=None, losses=None):
         """render_fwd + loss_partial in one launch (training path)."""
         rays_o, rays_d = _f32c(rays_o), _f32c(rays_d)
         perturb = self.perturb if perturb is None else int(perturb)
@@ -230,7 +230,7 @@ class FieldPlan:
                                               L.ptr(_f32c(target_d).reshape(-1)), rays_o.shape[0],
                                               L.ptr(_f32c(u)) if u is not None else None, perturb, seed,
                                               L.ptr(seed_step) if seed_step is not None else None, C.byref(cs),
-                                              L.ptr(stats), _stream()))
+                                              L.ptr(stats), L.ptr(losses) if losses is not None else None, _stream()))
         return out
 
     def new_stats(self, device):

@@ -82,17 +82,20 @@ class MappingStep:
     def _body(self, with_uncert_step: bool):
         """The launches of one iteration on the current stream.  Returns how many kernels of ours it launched."""
         p, n = self.plan, 0
+        fused_losses = self.losses if self.world == 1 else None      # one shard: the render kernel's last CTA finalizes the losses
         if self.external_random:                            # test hook: caller-written self.u / self.rand6 (the reference's draws)
             p.counter_add(self.map_step, 1); n += 1
-            p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=self.u); n += 1
+            p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=self.u,
+                               losses=fused_losses); n += 1
         else:
             # the reference's torch.rand(z_vals.shape), torch.rand(3), torch.rand((1,1,1,3)) draws, made on the device from Philox
             # keyed by (seed, step counter): nothing host-side changes between graph replays
             p.step_begin(self.map_step, self.seed, self.rand6 if self.smooth_on else None); n += 1
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=None,
-                               seed=self.seed, seed_step=self.map_step); n += 1
-        reduce_stats(self.stats, self.pg)
-        p.loss_finalize(self.stats, self.losses); n += 1
+                               seed=self.seed, seed_step=self.map_step, losses=fused_losses); n += 1
+        if fused_losses is None:                            # N > 1: the losses are ratios of GLOBAL sums
+            reduce_stats(self.stats, self.pg)
+            p.loss_finalize(self.stats, self.losses); n += 1
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,
                      self.G, workspace=self.ws_bwd); n += 2
         if self.smooth_on:                                  # ray-independent term: every rank takes one slab of the lattice
