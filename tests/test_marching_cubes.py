@@ -61,6 +61,16 @@ def test_triangle_table_is_a_valid_marching_cubes_table():
             assert set(row) == cut, c
 
 
+def test_committed_triangle_table_is_what_the_reference_triangulates_with():
+    """csrc/mc_tables.inc against the compiled reference probed one cube case at a time (oracle/probe_mc_tables.py)."""
+    from oracle import mc_ref
+    if not mc_ref.available():
+        pytest.skip('oracle/_ref/libmc_ref.so not built (needs /root/reference)')
+    from oracle.mc_oracle import tri_table
+    from oracle.probe_mc_tables import probe
+    assert tri_table() == probe()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('name', CASES)
 def test_kernel_matches_reference_golden(name):
