@@ -100,6 +100,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def cpu_reference(n_rays, steps, warmup, seed=0):
     import torch
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference arm uses all the host cores it can, whatever launched it
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     from oracle import naruto_oracle as no
     from naruto_b200.synthetic import SyntheticFrame
     spec = no.office0_spec(n_samples_d=N_SAMPLES_D)
@@ -144,7 +149,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n_rays = args.ref_rays
+    n_rays = args.ref_rays if args.ref_rays > 0 else args.rays
     total, threads = cpu_reference(n_rays, args.steps, args.warmup)
     val = n_rays * args.steps / total
     sample = f'{args.steps} full mapping iterations (fwd+loss+bwd+Adam) of {n_rays} rays x {S} samples on the host'
@@ -183,16 +188,102 @@ def time_kernels(plan, ms, torch, flush, reps=10):
             ts.append(a.elapsed_time(b))
         return statistics.median(ts)
 
-    res['render_fwd_ws_kernel'] = (timed(lambda: plan.render_fwd(ms.P, ms.rays_o, ms.rays_d, ms.target_d, ms.out, u=ms.u)),
+    # the launch the step itself makes: nrt_render_fwd_stats (features + ReLU masks saved, loss statistics fused, losses finalized)
+    res['render_fwd_ws_kernel'] = (timed(lambda: plan.render_fwd_stats(ms.P, ms.rays_o, ms.rays_d, ms.target_rgb, ms.target_d, ms.out,
+                                                                       ms.stats, u=None, seed=ms.seed, seed_step=ms.map_step,
+                                                                       losses=ms.losses)),
                                    B * BYTES_PER_RAY_FWD)
-    plan.loss_partial(ms.out, ms.target_rgb, ms.target_d, ms.stats)
-    plan.loss_finalize(ms.stats, ms.losses)
     gsave = ms.grad.clone()
     t_bwd = timed(lambda: plan.render_bwd(ms.P, ms.rays_o, ms.rays_d, ms.target_rgb, ms.target_d, ms.out, ms.stats, ms.loss_grad,
                                           ms.G, workspace=ms.ws_bwd))
     res['composite_bwd+decode_bwd_tc_kernel'] = (t_bwd, n_pts * BYTES_PER_POINT_BWD)
     ms.grad.copy_(gsave)
     return res
+
+
+def teardown(step_objs):
+    """Leave cleanly: CUDA graphs that captured NCCL collectives must be destroyed BEFORE the process group (otherwise
+    destroy_process_group() waits forever on the communicator the graphs still reference)."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    for m in step_objs:
+        m.release_graphs()
+    step_objs.clear()
+    gc.collect()
+    torch.cuda.synchronize()
+    if dist.is_available() and dist.is_initialized():
+        th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        th.start()
+        th.join(20)
+        if th.is_alive():                      # never hang the driver: report and leave
+            sys.stderr.write('bench.py: destroy_process_group() did not return within 20 s, exiting without it\n')
+            sys.stdout.flush()
+            os._exit(0)
+
+
+def side_config(name, cfg, bound, B_local, dev, pg, world, rank, scaling, steps=20, warmup=5):
+    """One of the other BASELINE.json configurations: CUDA-event time of the full mapping iteration (graph replay, L2 flushed
+    before every step, max over ranks) and of the forward launch alone on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from naruto_b200.field import FieldPlan, FieldTensors
+    from naruto_b200.mapper import MappingStep
+    from naruto_b200.synthetic import SyntheticFrame
+    plan = FieldPlan(cfg, bound)
+    g = torch.Generator().manual_seed(0)
+    lin = lambda o, i: (torch.rand(o, i, generator=g) * 2 - 1) / (i ** 0.5)
+    init = FieldTensors((torch.rand(plan.n_grid_floats, generator=g) * 2 - 1) * 1e-4, lin(32, 80), lin(16, 32), lin(32, 63),
+                        lin(3, 32), torch.full(plan.uncert_dims, 3.0))
+    ms = MappingStep(plan, cfg, B_local, dev, init=init, process_group=pg)
+    del init
+    frame = SyntheticFrame(bound, seed=300 + rank)
+    batches = [frame.sample_packed(B_local).to(dev) for _ in range(4)]
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    evs = []
+    for i in range(warmup + steps):
+        ms.load_packed(batches[i % 4])
+        flush_buf.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ms.step()
+        b.record()
+        if i == warmup - 1:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+        if i >= warmup:
+            evs.append((a, b))
+    torch.cuda.synchronize()
+    t = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    if world > 1:
+        tt = torch.tensor([t], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = tt.item()
+    Sn = plan.S
+    out = {'workload': name, 'rays_per_step_per_gpu': B_local, 'rays_per_step': B_local * world, 'samples_per_ray': Sn,
+           'table_MB': round(plan.n_grid_floats * 4 / 1e6, 1), 'scaling': scaling, 'steps': steps,
+           'ms_per_step': round(1e3 * t / steps, 4), 'rays_per_s': B_local * world * steps / t,
+           'losses_finite': bool(torch.isfinite(ms.losses[:5]).all().item())}
+    if rank == 0:
+        tf = []
+        for i in range(6):
+            flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            plan.render_fwd_stats(ms.P, ms.rays_o, ms.rays_d, ms.target_rgb, ms.target_d, ms.out, ms.stats, u=None, seed=ms.seed,
+                                  seed_step=ms.map_step, losses=ms.losses)
+            b.record()
+            b.synchronize()
+            tf.append(a.elapsed_time(b))
+        f = statistics.median(tf[1:])
+        hbm, _ = peaks()
+        gbs = B_local * (Sn * 1056 + 60) / f / 1e6
+        out.update({'fwd_ms': round(f, 4), 'fwd_algorithmic_GB_per_s': round(gbs, 1), 'fwd_frac_of_hbm_peak': round(gbs / hbm, 4)})
+    ms.release_graphs()
+    del ms, plan, flush_buf, batches
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args):
@@ -359,14 +450,27 @@ def run_ours(args):
         cpu = {'value': n_cpu * k_cpu / tot, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': f'{k_cpu} mapping iterations of {n_cpu} rays x {S} samples (oracle/naruto_oracle.py, torch CPU, '
                          f'{os.cpu_count()} host cpus)'}
+    side = None
+    if args.side_configs:
+        # BASELINE.json configs[2] (2 048-ray global batches split over the ranks: STRONG scaling; synthetic apartment-sized
+        # bound) and configs[3] (largest shipped MP3D bound, 2^21-entry levels = 154 MB table that does not
+        # fit L2, 192 samples/ray, 8 192 rays per GPU).  Every rank takes part (the iteration holds collectives).
+        from naruto_b200.configs import MP3D_LARGE_BOUND, mp3d_large
+        apartment = [[-8.0, 8.0], [-6.0, 6.0], [-1.5, 3.5]]
+        side = {}
+        if 2048 % world == 0:
+            side['apartment0_2048ray_batches'] = side_config(
+                'synthetic apartment_0-sized bound, 2048-ray GLOBAL batch split over the ranks, 43 samples/ray (32+11), hash_size 16',
+                replica_office0(n_samples_d=32, bound=apartment), apartment, 2048 // world, dev, pg, world, rank, 'strong')
+        side['mp3d_large_hash21_192samples'] = side_config(
+            'MP3D YmJkqBEsHnH bound, 2^21-entry levels (HBM-resident table), 8192 rays/GPU x 192 samples/ray (181+11)',
+            mp3d_large(), MP3D_LARGE_BOUND, 8192, dev, pg, world, rank, 'weak')
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
     if rank != 0:
-        # destroy_process_group() blocks forever once NCCL collectives have been captured into CUDA graphs
-        # (measured on this pool, torch 2.11 / NCCL 2.28): leave without the teardown
-        sys.stdout.flush()
-        os._exit(0)
+        teardown([ms])
+        return
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': 1e3 * t_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
@@ -386,10 +490,11 @@ def run_ours(args):
         line['torch_gpu_baseline'] = gpu_torch
     if cpu is not None:
         line['cpu_baseline'] = cpu
+    if side is not None:
+        line['configs'] = side
     print(json.dumps(line))
-    if world > 1:
-        sys.stdout.flush()
-        os._exit(0)             # see above: no destroy_process_group() after graph-captured collectives
+    sys.stdout.flush()
+    teardown([ms])
 
 
 def main():
@@ -398,17 +503,24 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--rays', type=int, default=4096, help='rays per GPU per mapping iteration')
-    ap.add_argument('--ref-rays', type=int, default=1024, help='rays per step for --impl reference')
+    ap.add_argument('--ref-rays', type=int, default=0, help='rays per step for --impl reference (0 = the same as --rays)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--sweep-rays', type=int, default=1 << 20, help='rays of the forward-only sweep (0 = skip)')
-    ap.add_argument('--torch-gpu-baseline', action='store_true',
-                    help='also time the oracle (reference Python path restated in torch ops) on the GPU')
+    ap.add_argument('--no-torch-gpu-baseline', dest='torch_gpu_baseline', action='store_false',
+                    help='skip timing the oracle (reference Python path restated in torch ops) on the GPU')
+    ap.add_argument('--no-side-configs', dest='side_configs', action='store_false',
+                    help='skip the BASELINE.json configs[2] / configs[3] side measurements')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.set_defaults(torch_gpu_baseline=True, side_configs=True)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == 'reference':
+        if args.steps > 10:
+            args.steps = 10          # bounded sample: ~1.5 s of host work per 4096-ray iteration
+        if args.warmup > 3:
+            args.warmup = 3
         run_reference(args)
     else:
         run_ours(args)

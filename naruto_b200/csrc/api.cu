@@ -53,6 +53,23 @@ int launch_umma_raw(const float*, int, const float*, int, int, int, int, int, in
 
 static thread_local char g_err[512] = "";
 
+int nrt_device_sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 148;
+  }
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    (void)cudaGetLastError();
+    return 148;
+  }
+  if (dev >= 0 && dev < 64) cached[dev] = sms;
+  return sms;
+}
+
 void nrt_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -108,7 +125,10 @@ int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
     }
     offset += size;
   }
-  NRT_REQUIRE(offset < (1ull << 31), "hash table too large for 32-bit entry offsets");
+  if (offset >= (1ull << 31)) {
+    delete p;
+    NRT_REQUIRE(false, "hash table too large for 32-bit entry offsets");
+  }
   p->n_grid_floats = (int64_t)offset * 2;
   for (int i = 0; i < 3; ++i) {
     d.bb_min[i] = cfg->bound_min[i];
@@ -127,13 +147,7 @@ int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
   d.step_u = d.n_d > 1 ? (d.far_z - d.near_z) / (float)(d.n_d - 1) : 0.f;
   d.step_r = d.n_r > 1 ? (d.range_d - (-d.range_d)) / (float)(d.n_r - 1) : 0.f;
   d.step_n = d.n_r > 1 ? (d.far_z - d.near_z) / (float)(d.n_r - 1) : 0.f;
-  p->sm_count = 148;
-  int dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
-    int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) p->sm_count = sms;
-  }
-  (void)cudaGetLastError();   // plan creation is legal without a device (CPU-side symbol/level tests)
+  p->sm_count = nrt_device_sm_count();   // plan creation is legal without a device (CPU-side symbol/level tests): 148 then
   *out = p;
   return NRT_OK;
 }
@@ -294,7 +308,7 @@ int nrt_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   const int32_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay, int zero_grad,
                   void* stream) {
   NRT_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev), "adam arguments");
-  int sms = 148;
+  const int sms = nrt_device_sm_count();
   return launch_adam(param, grad, exp_avg, exp_avg_sq, n, step, step_dev, lr, beta1, beta2, eps, weight_decay, zero_grad, sms,
                      (cudaStream_t)stream);
 }
@@ -333,11 +347,7 @@ int nrt_goal_aggregate(const float* uncert_vol, const float* sdf_vol, const int3
   NRT_REQUIRE(dims && dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && n_goal >= 0 && k >= 0, "goal_aggregate sizes");
   NRT_REQUIRE(n_goal == 0 || (uncert_vol && sdf_vol && goal_pts && aggre && (k == 0 || (topk_vxl && collections))),
               "goal_aggregate arguments");
-  int sms = 148, dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
-  }
+  const int sms = nrt_device_sm_count();
   return launch_goal_aggregate(uncert_vol, sdf_vol, dims, goal_pts, n_goal, topk_vxl, k, min_dist, max_dist, safe_sdf, collections,
                                aggre, n_valid, sms, (cudaStream_t)stream);
 }
@@ -346,11 +356,7 @@ int nrt_erp_depth2dist(const float* erp_depth, int32_t H, int32_t W, const float
                        const float* face_rays, int32_t skybox_size, float* erp_dist, void* stream) {
   NRT_REQUIRE(H >= 0 && W >= 0 && skybox_size >= 2, "erp_depth2dist sizes");
   NRT_REQUIRE((int64_t)H * W == 0 || (erp_depth && c2e_grid && face_coor && face_rays && erp_dist), "erp_depth2dist arguments");
-  int sms = 148, dev = 0;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
-    int v = 0;
-    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
-  }
+  const int sms = nrt_device_sm_count();
   return launch_erp_depth2dist(erp_depth, H, W, c2e_grid, face_coor, face_rays, skybox_size, erp_dist, sms, (cudaStream_t)stream);
 }
 

@@ -180,10 +180,9 @@ __global__ void __launch_bounds__(256) encode_bwd_kernel(const __grid_constant__
 int launch_composite_bwd(const NrtPlan* plan, const NrtRenderOut* rend, const float* target_rgb, const float* target_d,
                          int64_t n_rays, const double* stats, const float* loss_grad, float* draw, cudaStream_t st) {
   const size_t smem = (size_t)8 * plan->dev.S * 7 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     NRT_CUDA_CHECK(cudaFuncSetAttribute(composite_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_set = true;
   }
   int64_t blocks = (n_rays + 7) / 8;
   int64_t cap = (int64_t)plan->sm_count * 8;

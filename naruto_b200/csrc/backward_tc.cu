@@ -455,11 +455,10 @@ int launch_decode_bwd(const NrtPlan* plan, const NrtParams* prm, const PointSour
   if (n_pts == 0) return NRT_OK;
   const bool saved = masks != nullptr;
   const size_t smem = decode_bwd_tc_smem(saved);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     NRT_CUDA_CHECK(cudaFuncSetAttribute(decode_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_bwd_tc_smem(true)));
     NRT_CUDA_CHECK(cudaFuncSetAttribute(decode_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_bwd_tc_smem(false)));
-    attr_set = true;
   }
   const int64_t tiles = (n_pts + 127) / 128;
   const int blocks = (int)(tiles < plan->sm_count ? tiles : plan->sm_count);

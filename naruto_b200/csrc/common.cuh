@@ -653,6 +653,21 @@ __device__ __forceinline__ void finalize_losses(const double* stats, float* __re
 
 // error plumbing (api.cu)
 void nrt_set_error(const char* fmt, ...);
+// SM count of the current device (cached per device; 148 if there is none)
+int nrt_device_sm_count();
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: one flag per (call site, device), so a process
+// that drives several GPUs sets it on each of them.  Racing threads at worst set the attribute twice.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
 #define NRT_CUDA_CHECK(expr)                                                          \
   do {                                                                                \
     cudaError_t _e = (expr);                                                          \

@@ -294,11 +294,10 @@ static const size_t kPointsSmem = 80 * 1024;
 int launch_decode_fwd(const NrtPlan* plan, const NrtParams* prm, const float* x, int64_t n, int with_color, float* raw,
                       float* sdf_uncert, float* geo, cudaStream_t st) {
   if (n == 0) return NRT_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     NRT_CUDA_CHECK(cudaFuncSetAttribute(points_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPointsSmem));
     NRT_CUDA_CHECK(cudaFuncSetAttribute(points_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPointsSmem));
-    attr_set = true;
   }
   const int64_t tiles = (n + 127) / 128;
   const int blocks = (int)(tiles < 2 * plan->sm_count ? tiles : 2 * plan->sm_count);
@@ -314,10 +313,9 @@ int launch_decode_fwd(const NrtPlan* plan, const NrtParams* prm, const float* x,
 // dense uncertainty + SDF sweep over the lattice of get_map_volumes; dims = lattice points per axis
 int launch_map_volumes(const NrtPlan* plan, const NrtParams* prm, const int* dims, float* vol_uncert, float* vol_sdf,
                        cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     NRT_CUDA_CHECK(cudaFuncSetAttribute(points_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPointsSmem));
-    attr_set = true;
   }
   LatticeSrc lat{};
   for (int a = 0; a < 3; ++a) {
@@ -373,10 +371,9 @@ int launch_render_fwd(const NrtPlan* plan, const NrtParams* prm, const float* ra
   // carve-out is forced to the full 228 KB; and any static shared memory in this kernel tips it over that edge.
   size_t smem = TC_SMEM_WEIGHTS + (size_t)rpu * (6 + 6 * S) * sizeof(float);
   if (smem < kPointsSmem) smem = kPointsSmem;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    attr_set = true;
   }
   const int blocks = (int)(units < slots ? units : slots);
   render_fwd_tc_kernel<<<blocks, TC_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb, seed,

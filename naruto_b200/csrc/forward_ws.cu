@@ -406,11 +406,10 @@ int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float*
   if (rpu < 1) rpu = 1;
   const int64_t units = (n_rays + rpu - 1) / rpu;
   const size_t smem = TC_SMEM_WEIGHTS + (size_t)(2 * WS_NST * WS_STAGE_FLOATS + 2 * rpu * (6 + 6 * S)) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     NRT_CUDA_CHECK(cudaFuncSetAttribute(render_fwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const int64_t want = (units + 1) / 2;
   const int blocks = (int)(want < plan->sm_count ? want : plan->sm_count);

@@ -102,6 +102,11 @@ class FieldPlan:
                 or not d.get('uncert_grid', False) or t.get('n_importance', 0) > 0 or not cfg['grid'].get('tcnn_encoding', True):
             raise L.NrtError('naruto_b200 implements the shipped NARUTO configuration: oneGrid, nn.Linear decoders, '
                              'uncert_grid, n_importance=0, tcnn_encoding')
+        if float(t.get('rgb_missing', 0.05)) == 0.0:
+            # src/slam/coslam/model/scene_rep.py:249-250 writes rgb_missing into a BOOL weight tensor: every non-zero value
+            # becomes True (weight 1) -- what the kernels implement -- but 0.0 would really mask rays
+            raise L.NrtError('training.rgb_missing == 0 is not implemented (the one value for which the reference\'s bool '
+                             'rgb_weight masks rays; shipped configs use 0.05)')
         self.c = L.NrtConfig(
             abi_version=L.NRT_ABI_VERSION, n_levels=n_levels, n_features=2, log2_hashmap_size=int(cfg['grid']['hash_size']),
             base_resolution=base, per_level_scale=self.per_level_scale, n_bins=int(cfg['pos']['n_bins']),

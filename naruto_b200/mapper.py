@@ -22,6 +22,10 @@ class MappingStep:
         self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         t, mp = cfg['training'], cfg['mapping']
+        if int(mp.get('map_accum_step', 1)) != 1 or int(mp.get('map_wait_step', 0)) != 0:
+            # src/slam/coslam/coslam.py:368-376: the reference steps the optimiser every map_accum_step iterations after
+            # map_wait_step; the fused iteration steps every time (1 / 0 at every shipped config)
+            raise L.NrtError('MappingStep implements mapping.map_accum_step == 1 and map_wait_step == 0 (the shipped values)')
         self.lr_decoder, self.lr_embed = float(mp['lr_decoder']), float(mp['lr_embed'])
         self.smooth_on = bool(smooth) and t['smooth_weight'] > 0
         self.smooth_w, self.smooth_n = float(t['smooth_weight']), int(t['smooth_pts'])
@@ -74,7 +78,11 @@ class MappingStep:
         self.it = 0
         self.use_graph = use_graph
         self.external_random = False     # test hook: keep caller-written self.u / self.rand6 instead of drawing
-        self.seed = 0x9E3779B9 + 7919 * self.rank          # per-rank jitter stream (RNG must be rank-offset)
+        # two Philox keys: the stratified jitter is per ray, so its stream is rank-offset; the smoothness lattice
+        # draw (rand6) must be THE SAME on every rank -- each rank takes one slab of one common lattice, and only then do the
+        # slabs add up to the reference's smoothness() term in the gradient all-reduce
+        self.base_seed = 0x9E3779B9
+        self.seed = self.base_seed + 7919 * self.rank
         self._graphs = {}
         self.launches_per_iter = {False: 0, True: 0}
 
@@ -90,7 +98,7 @@ class MappingStep:
         else:
             # the reference's torch.rand(z_vals.shape), torch.rand(3), torch.rand((1,1,1,3)) draws, made on the device from Philox
             # keyed by (seed, step counter): nothing host-side changes between graph replays
-            p.step_begin(self.map_step, self.seed, self.rand6 if self.smooth_on else None); n += 1
+            p.step_begin(self.map_step, self.base_seed, self.rand6 if self.smooth_on else None); n += 1
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=None,
                                seed=self.seed, seed_step=self.map_step, losses=fused_losses); n += 1
         if fused_losses is None:                            # N > 1: the losses are ratios of GLOBAL sums
@@ -137,6 +145,11 @@ class MappingStep:
         return self._graphs[with_uncert_step]
 
     # -------------------------------------------------------------------------------------------
+    def release_graphs(self):
+        """Destroy the captured CUDA graphs (they hold references to the NCCL communicator: do this before
+        torch.distributed.destroy_process_group())."""
+        self._graphs.clear()
+
     def load_rays(self, rays_o, rays_d, target_rgb, target_d):
         """Host (pinned) or device tensors -> the static input buffers (async copies on the current stream)."""
         self.rays_o.copy_(rays_o.reshape(self.B, 3), non_blocking=True)

@@ -254,6 +254,32 @@ class JointEncodingNaruto(nn.Module):
         o = self.plan.composite_fwd(raw, z_vals)
         return o.rgb, o.disp, o.acc, o.weights, o.depth, o.depth_var, o.uncert
 
+    # ---- inactive-at-shipped-config surface: present, explicit ---------------------------------
+    def get_resolution(self):
+        """tp/model/scene_rep.py:20-35: resolution_sdf from grid.voxel_sdf (done by FieldPlan at construction)."""
+        self.resolution_sdf = self.plan.resolution_sdf
+        return self.resolution_sdf
+
+    def render_surface_color(self, rays_o, normal):
+        """tp/model/scene_rep.py:180-196: colour of surface points from n_range_d samples along +-trunc of the normal.
+        (In the reference this method unpacks six values from JointEncodingNaruto.raw2outputs, which returns seven, so it
+        raises ValueError there; `training.render_color` is False at every shipped config.  Served here by the same
+        kernels as render_rays: point decode + compositor.)"""
+        _require_cuda(rays_o, 'rays_o')
+        with torch.no_grad():
+            t = self.config['training']
+            z = torch.linspace(-t['trunc'], t['trunc'], steps=t['n_range_d']).to(rays_o).repeat(rays_o.shape[0], 1)
+            pts = rays_o[..., :] + normal[..., None, :] * z[..., :, None]
+            raw = self.run_network(pts)
+            return self.plan.composite_fwd(raw, z, want_weights=False).rgb
+
+    @staticmethod
+    def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
+        """tp/model/utils.py:29-68 (hierarchical importance sampling).  Only reached with training.n_importance > 0, which
+        FieldPlan rejects at construction (0 at every shipped config): there is no kernel for it and no torch fallback."""
+        raise L.NrtError('sample_pdf / n_importance > 0 is not implemented by naruto_b200 (n_importance is 0 at every shipped '
+                         'NARUTO config); FieldPlan rejects such a config at construction')
+
     # ---- rays --------------------------------------------------------------------------------------
     def render_rays(self, rays_o, rays_d, target_d=None, u=None, z_vals=None):
         """src/slam/coslam/model/scene_rep.py:150-225.  `u` ([B,S] uniform draws) / `z_vals` are optional parity hooks:
@@ -274,6 +300,13 @@ class JointEncodingNaruto(nn.Module):
         if not self.training:
             return self.render_rays(rays_o, rays_d, target_d=target_d, u=u)
         _require_cuda(rays_o, 'rays_o')
+        if rays_o.requires_grad or rays_d.requires_grad:
+            # the reference lets dL/d rays flow into the pose parameters (src/slam/coslam/coslam.py:265,342-344); this
+            # library has no d rays_o / d rays_d output, and NARUTO runs with tracking / pose refinement disabled
+            # (poses are ground truth, `cur_rot`/`cur_trans` never receive an optimiser step): refuse instead of
+            # silently detaching.
+            raise L.NrtError('naruto_b200: rays_o / rays_d require grad, but the fused renderer has no pose gradient '
+                             '(NARUTO maps with fixed poses); pass detached rays')
         f = lambda t: t.detach().float().contiguous()
         losses, rgb, depth = _RenderLossFn.apply(self.plan, f(rays_o), f(rays_d), f(target_rgb), f(target_d), u,
                                                  self._next_seed(), *self._tensors().as_list())
