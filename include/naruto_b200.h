@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define NRT_ABI_VERSION 2
+#define NRT_ABI_VERSION 3
 
 typedef enum NrtStatus {
   NRT_OK = 0,
@@ -112,9 +112,10 @@ typedef struct NrtRenderOut {
   float* weights;     /* dev [B,S] */
   float* feat;        /* dev, ceil(B*S/128)*128*32 floats: hash features saved for nrt_render_bwd (training), opaque tile-major
                        * layout [tile of 128 points][8 chunks][128 points][4 floats] (coalesced for writer and reader) */
-  uint32_t* masks;    /* dev [B*S,2] ReLU masks of the two hidden layers (bit j = unit j active), saved for nrt_render_bwd:
-                       * with them the backward recomputes activations in single-pass TF32 (they only feed the tf32
-                       * weight-gradient operands) instead of 3xTF32; optional (NULL: masks are recomputed exactly) */
+  uint32_t* masks;    /* dev [ceil(B*S/128)*128, 2] (padded to whole tiles like feat; rows >= B*S are never read as data) ReLU
+                       * masks of the two hidden layers (bit j = unit j active), saved for nrt_render_bwd: with them the
+                       * backward recomputes activations in single-pass TF32 (they only feed the tf32 weight-gradient
+                       * operands) instead of 3xTF32 and fetches its tiles by TMA; optional (NULL: masks are recomputed exactly) */
 } NrtRenderOut;
 
 #define NRT_N_LOSS 8
@@ -291,6 +292,10 @@ int nrt_active_select(const float* rays_o, const float* rays_d, const float* tar
  *   mode 1: d[k,n]   = a[128 rows,k]^T * b[128 rows,n]  (weight-gradient form, k <= 128 valid output rows, passes = 1)
  *   mode 2: as mode 0 with the A operand staged in tensor memory
  * passes = 1 (plain TF32) or 3 (hi/lo split, ~fp32 accuracy).  d always has 128 rows. */
+/* Profiling aid: with NRT_BWD_DEBUG=8 in the environment the backward kernel stamps clock64() at its phase boundaries
+ * (per CTA: entry, prologue done, MLP loop done, scatter loop done, before flush, after flush, end); this copies the
+ * [256][8] int64 table to host memory (synchronises). */
+int nrt_debug_read(void* host_dst, int32_t bytes);
 int nrt_selftest_umma(int mode, const float* a, const float* b, int32_t k, int32_t n, int passes, float* d, void* stream);
 /* Raw probe: a_img / b_img (dev) are copied verbatim into shared memory and multiplied as d[128,n] with the given
  * descriptor fields (bytes): leading / stride byte offsets, per-k-step start-address advance, MN-major flags. */
@@ -338,6 +343,13 @@ void nrt_mc_result_free(void* result);
  * Backprojection (src/layers/backprojection.py:31-82) with K = diag-ish(s/2). */
 int nrt_erp_depth2dist(const float* erp_depth, int32_t H, int32_t W, const float* c2e_grid, const float* face_coor,
                        const float* face_rays, int32_t skybox_size, float* erp_dist, void* stream);
+/* The same conversion without look-up grids: every grid entry above is a closed-form function of the output pixel and is
+ * evaluated in the kernel (C2E.__init__ src/layers/c2e.py:82-130 with equirect_uvgrid / equirect_facetype
+ * src/layers/c2e_utils.py:68-93; create_erp_coor src/layers/erp_conversions.py:184-229; Backprojection
+ * src/layers/backprojection.py:31-82).  face_rot: HOST fp32 [6,3,3], row-vector frames of the faces F R B L U D
+ * (p_panorama = [x, -y, 1] @ face_rot[f]); x_max = tan(fov/2) of a face (1 for the 90-degree skybox).  W % 4 == 0. */
+int nrt_erp_depth2dist_analytic(const float* erp_depth, int32_t H, int32_t W, int32_t skybox_size, const float* face_rot,
+                                float x_max, float* erp_dist, void* stream);
 
 #ifdef __cplusplus
 }

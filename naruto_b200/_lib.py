@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libnaruto_b200.so')
 
-NRT_ABI_VERSION = 2
+NRT_ABI_VERSION = 3
 N_LOSS = 8
 N_STATS = 16
 N_STATS_SUM = 11
@@ -71,6 +71,8 @@ SIGNATURES = {
     'nrt_goal_aggregate': (C.c_int, [c_fp, c_fp, C.POINTER(C.c_int32), c_fp, C.c_int64, c_fp, C.c_int32, C.c_float, C.c_float,
                                      C.c_float, c_fp, c_fp, c_fp, _P]),
     'nrt_erp_depth2dist': (C.c_int, [c_fp, C.c_int32, C.c_int32, c_fp, c_fp, c_fp, C.c_int32, c_fp, _P]),
+    'nrt_erp_depth2dist_analytic': (C.c_int, [c_fp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_float, c_fp, _P]),
+    'nrt_debug_read': (C.c_int, [C.c_void_p, C.c_int32]),
     'nrt_loss_stats_bytes': (C.c_int64, []),
     'nrt_loss_partial': (C.c_int, [_P, C.POINTER(NrtRenderOut), c_fp, c_fp, C.c_int64, c_fp, _P]),
     'nrt_loss_finalize': (C.c_int, [_P, c_fp, c_fp, _P]),

@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -23,8 +24,12 @@ int launch_composite_bwd(const NrtPlan*, const NrtRenderOut*, const float*, cons
                          float*, cudaStream_t);
 int launch_decode_bwd(const NrtPlan*, const NrtParams*, const PointSource&, int64_t, const float*, int, const uint32_t*, const float*, float*,
                       const NrtGrads*, cudaStream_t);
+int launch_decode_bwd_q(const NrtPlan*, const NrtParams*, const float*, const float*, const float*, int, int64_t, const float*,
+                        const uint32_t*, const float*, const NrtGrads*, float*, cudaStream_t);
+int64_t decode_bwd_q_scratch_floats(const NrtPlan*);
 int launch_encode_bwd(const NrtPlan*, const float*, const PointSource&, int64_t, const float*, float, float*, float*,
                       cudaStream_t);
+int q_trace_read(void*, int);
 int launch_smooth(const NrtPlan*, const float*, const float*, int, double, double, float, float*, float*, void*, int, int, cudaStream_t);
 int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
                 cudaStream_t);
@@ -39,6 +44,7 @@ void mc_release(void*);
 int launch_goal_aggregate(const float*, const float*, const int*, const float*, int64_t, const float*, int, float, float, float,
                           float*, float*, int*, int, cudaStream_t);
 int launch_erp_depth2dist(const float*, int, int, const float*, const float*, const float*, int, float*, int, cudaStream_t);
+int launch_erp_depth2dist_analytic(const float*, int, int, int, const float*, float, float*, int, cudaStream_t);
 int launch_camera_rays(int, int, float, float, float, float, float*, cudaStream_t);
 int launch_pack_frame(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
 int launch_valid_depth_count(const float*, int64_t, float, int*, cudaStream_t);
@@ -181,6 +187,7 @@ int nrt_encode_fwd(const NrtPlan* plan, const float* grid, const float* x, int64
 int nrt_encode_bwd(const NrtPlan* plan, const float* grid, const float* x, int64_t n, const float* dout, float* dgrid,
                    float* dx, void* stream) {
   NRT_REQUIRE(plan && grid && n >= 0 && (n == 0 || (x && dout)), "encode_bwd arguments");
+  NRT_REQUIRE((reinterpret_cast<uintptr_t>(dgrid) & 15u) == 0, "dgrid must be 16-byte aligned (paired 16-byte reductions)");
   PointSource src{x, nullptr, nullptr, nullptr, 1};
   return launch_encode_bwd(plan, grid, src, n, dout, 1.0f, dgrid, dx, (cudaStream_t)stream);
 }
@@ -273,7 +280,9 @@ int nrt_decode_bwd(const NrtPlan* plan, const NrtParams* params, const float* x,
 
 int64_t nrt_render_bwd_workspace(const NrtPlan* plan, int64_t n_rays) {
   if (!plan || n_rays < 0) return 0;
-  return n_rays * plan->dev.S * 5 * (int64_t)sizeof(float);      // dL/d raw; feature gradients stay on chip
+  // dL/d raw, padded to whole tiles of 128 points (the backward kernel fetches it tile-wise by TMA); feature gradients stay on chip
+  // + one weight-gradient block per CTA, reduced in fixed order by the second launch of the backward
+  return ((n_rays * plan->dev.S + 127) / 128 * 128 * 5 + decode_bwd_q_scratch_floats(plan)) * (int64_t)sizeof(float);
 }
 
 int nrt_render_bwd(const NrtPlan* plan, const NrtParams* params, const float* rays_o, const float* rays_d,
@@ -282,11 +291,20 @@ int nrt_render_bwd(const NrtPlan* plan, const NrtParams* params, const float* ra
   NRT_REQUIRE(plan && rays_o && rays_d && target_rgb && target_d && rend && stats && loss_grad && grads && workspace && n_rays > 0,
               "render_bwd arguments");
   NRT_REQUIRE(rend->z_vals && rend->raw && rend->feat, "render_bwd needs z_vals, raw and feat saved by render_fwd");
+  NRT_REQUIRE((reinterpret_cast<uintptr_t>(grads->grid) & 15u) == 0, "grads->grid must be 16-byte aligned (paired 16-byte reductions)");
   if (int rc = check_params(params)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n_pts = n_rays * plan->dev.S;
   float* draw = reinterpret_cast<float*>(workspace);
   if (int rc = launch_composite_bwd(plan, rend, target_rgb, target_d, n_rays, stats, loss_grad, draw, st)) return rc;
+  // saved masks: the 32-warp TMA-fed kernel (backward_q.cu); NRT_BWD_IMPL=tc selects round 1's kernel for A/B runs
+  static const bool use_tc = [] {
+    const char* e = getenv("NRT_BWD_IMPL");
+    return e && strcmp(e, "tc") == 0;
+  }();
+  if (rend->masks && !use_tc)
+    return launch_decode_bwd_q(plan, params, rays_o, rays_d, rend->z_vals, plan->dev.S, n_pts, rend->feat, rend->masks, draw, grads,
+                               draw + (n_pts + 127) / 128 * 128 * 5, st);
   PointSource src{nullptr, rays_o, rays_d, rend->z_vals, plan->dev.S};
   return launch_decode_bwd(plan, params, src, n_pts, rend->feat, 1, rend->masks, draw, nullptr, grads, st);
 }
@@ -301,6 +319,7 @@ int nrt_smooth_fwd_bwd(const NrtPlan* plan, const float* grid, const float* rand
                        float loss_scale, float* loss, float* dgrid, void* workspace, int32_t part, int32_t n_parts, void* stream) {
   NRT_REQUIRE(plan && grid && rand6 && loss && workspace && n >= 2, "smooth arguments");
   NRT_REQUIRE(n_parts >= 1 && part >= 0 && part < n_parts, "smooth: 0 <= part < n_parts");
+  NRT_REQUIRE((reinterpret_cast<uintptr_t>(dgrid) & 15u) == 0, "dgrid must be 16-byte aligned (paired 16-byte reductions)");
   return launch_smooth(plan, grid, rand6, n, voxel, margin, loss_scale, loss, dgrid, workspace, part, n_parts, (cudaStream_t)stream);
 }
 
@@ -358,6 +377,14 @@ int nrt_erp_depth2dist(const float* erp_depth, int32_t H, int32_t W, const float
   NRT_REQUIRE((int64_t)H * W == 0 || (erp_depth && c2e_grid && face_coor && face_rays && erp_dist), "erp_depth2dist arguments");
   const int sms = nrt_device_sm_count();
   return launch_erp_depth2dist(erp_depth, H, W, c2e_grid, face_coor, face_rays, skybox_size, erp_dist, sms, (cudaStream_t)stream);
+}
+
+int nrt_erp_depth2dist_analytic(const float* erp_depth, int32_t H, int32_t W, int32_t skybox_size, const float* face_rot, float x_max,
+                                float* erp_dist, void* stream) {
+  NRT_REQUIRE(H >= 0 && W >= 0 && skybox_size >= 2 && face_rot, "erp_depth2dist_analytic sizes");
+  NRT_REQUIRE((int64_t)H * W == 0 || (erp_depth && erp_dist && W % 4 == 0 && W >= 8 && H >= 2), "erp_depth2dist_analytic arguments");
+  return launch_erp_depth2dist_analytic(erp_depth, H, W, skybox_size, face_rot, x_max, erp_dist, nrt_device_sm_count(),
+                                        (cudaStream_t)stream);
 }
 
 int nrt_step_begin(int32_t* counter_dev, int32_t delta, uint64_t seed, float* rand6_dev, void* stream) {
@@ -426,6 +453,11 @@ int nrt_active_select(const float* rays_o, const float* rays_d, const float* tar
   return launch_active_select(rays_o, rays_d, target_s, target_d, n_rays, n_cur, uncert_vol, vol_dims[0], vol_dims[1], vol_dims[2],
                               bound_min, base_sample_num, num_uncert_sample, oversample_mul, out_o, out_d, out_s, out_t, chosen,
                               workspace, (cudaStream_t)stream);
+}
+
+int nrt_debug_read(void* host_dst, int32_t bytes) {
+  NRT_REQUIRE(host_dst && bytes >= 0, "debug_read arguments");
+  return q_trace_read(host_dst, bytes);
 }
 
 int nrt_selftest_umma(int mode, const float* a, const float* b, int32_t k, int32_t n, int passes, float* d, void* stream) {

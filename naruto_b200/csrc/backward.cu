@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) encode_bwd_kernel(const __grid_constant__
     if (dgrid && nz) {
       float2* base = dgrid + L.offset;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) red_add_f2(base + idx[c], w[c] * g0, w[c] * g1);
+      for (int c = 0; c < 8; c += 2) red_add_xpair(base, idx[c], idx[c + 1], w[c] * g0, w[c] * g1, w[c + 1] * g0, w[c + 1] * g1);
     }
     if (dx) {
       // d out/d x_d = scale * sign_d * prod_{d' != d} w_d' * value

@@ -66,6 +66,25 @@ __device__ __forceinline__ void red_add_f2(float2* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
+__device__ __forceinline__ void red_add_f4(float4* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// The two x-neighbour corner entries i0 / i1 of a cell (relative to the level's first entry `base`, which is 16-byte aligned:
+// level offsets are multiples of 8 entries).  Measured on B200 (tools/micro/red_throughput.cu): a no-return reduction costs
+// 0.79 ns per LANE per SM whether the lane carries 4, 8 or 16 bytes, and the backward scatter is bound by exactly that.  When
+// the two entries are the halves of one aligned 16-byte pair -- dense levels with an even base index, and every hashed level
+// at even x, because tcnn's coherent hash multiplies x by 1 so x -> x + 1 only flips the lowest index bit -- one v4 reduction
+// carries both: 6 instead of 8 lanes per point and level on average.
+__device__ __forceinline__ void red_add_xpair(float2* base, uint32_t i0, uint32_t i1, float a0, float a1, float b0, float b1) {
+  if ((i0 ^ i1) == 1u) {
+    const bool sw = (i0 & 1u) != 0u;
+    red_add_f4(reinterpret_cast<float4*>(base + (i0 & ~1u)), sw ? b0 : a0, sw ? b1 : a1, sw ? a0 : b0, sw ? a1 : b1);
+  } else {
+    red_add_f2(base + i0, a0, a1);
+    red_add_f2(base + i1, b0, b1);
+  }
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float softplusf_(float x) {

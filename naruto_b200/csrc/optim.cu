@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) smooth_tv_bwd_kernel(const __grid_constan
       level_corners(L, x0, x1, x2, e, w);
       float2* base = dgrid + L.offset;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) red_add_f2(base + e[c], w[c] * g.x, w[c] * g.y);
+      for (int c = 0; c < 8; c += 2)          // x-neighbour corners share one 16-byte reduction when aligned (common.cuh)
+        red_add_xpair(base, e[c], e[c + 1], w[c] * g.x, w[c] * g.y, w[c + 1] * g.x, w[c + 1] * g.y);
     }
     tv *= inv;
   }

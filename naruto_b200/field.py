@@ -63,7 +63,7 @@ class RenderBuffers:
         self.weights = torch.empty(B, S, **f) if weights else None
         # saved hash features, tile-major (see NrtRenderOut::feat): padded to whole tiles of 128 points
         self.feat = torch.zeros((B * S + 127) // 128 * 128, ENC_DIMS, **f) if feat else None
-        self.masks = torch.empty(B * S, 2, dtype=torch.int32, device=device) if feat else None      # ReLU masks, saved with feat
+        self.masks = torch.zeros((B * S + 127) // 128 * 128, 2, dtype=torch.int32, device=device) if feat else None   # ReLU masks (padded like feat)
 
     def feat_rows(self):
         """The saved hash features as a plain [B*S, 32] tensor (un-tiles NrtRenderOut::feat; diagnostics and tests)."""

@@ -22,18 +22,63 @@ def test_oracle_matches_reference_golden(tag):
     assert torch.equal(out, c['dist'])
 
 
+def _closed_form_grids(s, hw):
+    """numpy evaluation of the closed forms csrc/erp.cu:erp_depth2dist_analytic_kernel computes per pixel (same dtypes and
+    op order), tabulated so that they can be held against the grids the reference's constructor builds."""
+    from naruto_b200.erp import face_frames
+    H, W = hw
+    f32 = np.float32
+    lon = np.linspace(-np.pi, np.pi, W).astype(f32)[None, :].repeat(H, 0)
+    lat = (np.linspace(np.pi, -np.pi, H).astype(f32) * f32(0.5))[:, None].repeat(W, 1)
+    jj = (np.arange(W) - (3 * W) // 8) % W
+    band, col = jj // (W // 4), jj % (W // 4)
+    edge = np.linspace(-np.pi, np.pi, W // 4)[col] / 4.0
+    cap_rows = H // 2 - np.rint(np.arctan(np.cos(edge)) * H / np.pi).astype(int)
+    ii = np.arange(H)[:, None]
+    face = np.where((H - 1 - ii) < cap_rows[None, :], 5, np.where(ii < cap_rows[None, :], 4, band[None, :].repeat(H, 0)))
+    cx, cy = np.zeros((H, W), f32), np.zeros((H, W), f32)
+    for f in range(4):
+        m = face == f
+        a = lon[m] - f32(np.pi * f / 2)
+        cx[m] = f32(0.5) * np.tan(a)
+        cy[m] = (f32(-0.5) * np.tan(lat[m])) / np.cos(a)
+    for f, sgn in ((4, 1.0), (5, -1.0)):
+        m = face == f
+        c0 = f32(0.5) * np.tan(f32(np.pi / 2) - (lat[m] if f == 4 else np.abs(lat[m])))
+        cx[m] = c0 * np.sin(lon[m])
+        cy[m] = f32(sgn) * c0 * np.cos(lon[m])
+    X = (np.clip(cx.astype(np.float64), -0.5, 0.5) + 0.5) * (s - 1)
+    Y = (np.clip(cy.astype(np.float64), -0.5, 0.5) + 0.5) * (s - 1)
+    c2e = np.stack([(X / (s - 1) * 2 - 1).astype(f32), (Y / (s - 1) * 2 - 1).astype(f32), (face / 5 * 2 - 1).astype(f32)], -1)
+    # tangent-plane points of every texel, rotated by the face frames, to panorama coordinates
+    lad = torch.linspace(-1.0, 1.0, s).numpy()
+    px, py = np.meshgrid(lad, -lad, indexing='xy')
+    p = np.stack([px, py, np.ones_like(px)], -1).astype(f32)
+    coor = []
+    for M in face_frames():
+        q = p @ M
+        plon = np.arctan2(q[..., 0], q[..., 2])
+        plat = np.arctan2(q[..., 1], np.sqrt(q[..., 0] ** 2 + q[..., 2] ** 2))
+        ex = (plon / f32(2 * np.pi) + f32(0.5)) * f32(W) - f32(0.5)
+        ey = (-plat / f32(np.pi) + f32(0.5)) * f32(H) - f32(0.5)
+        coor.append(np.stack([ex / f32(W - 1) * f32(2) - f32(1), ey / f32(H - 1) * f32(2) - f32(1)], -1))
+    t = np.arange(s, dtype=f32)
+    r = f32(2.0) / f32(s) * t - f32(1)
+    rays = np.stack([np.tile(r, s), np.repeat(r, s), np.ones(s * s, f32)])
+    return torch.from_numpy(c2e), torch.from_numpy(np.stack(coor).astype(f32)), torch.from_numpy(rays)
+
+
 @pytest.mark.parametrize('tag', ['a', 'b'])
-def test_host_grids_match_reference_constructor(tag):
-    """The three static grids the drop-in builds on the host == the ones the reference's constructor builds."""
-    from naruto_b200 import erp
+def test_closed_forms_match_reference_constructor(tag):
+    """What the analytic kernel evaluates per pixel == the three grids the reference's constructor tabulates (its own
+    tensors, from the golden file): face ids exactly, coordinates to 2e-6."""
     c = _case(tag)
     s, hw = c['s'], tuple(c['depth'].shape)
-    coor = torch.stack([erp.face_sampling_grid(u, v, hw, s) for u, v in zip(erp._FACE_U_DEG, erp._FACE_V_DEG)])
+    c2e, coor, rays = _closed_form_grids(s, hw)
+    assert torch.equal(c2e[..., 2], c['c2e'][..., 2]), 'face ids'
+    assert (c2e - c['c2e']).abs().max() <= 2e-6
     assert (coor - c['coor']).abs().max() <= 2e-6
-    assert torch.equal(erp.texel_rays(s), c['rays'])
-    g = erp.cube_to_pano_grid(s, hw)
-    assert torch.equal(g[..., 2], c['c2e'][..., 2]), 'face ids'
-    assert (g - c['c2e']).abs().max() <= 2e-6
+    assert (rays - c['rays']).abs().max() <= 2e-6
 
 
 def test_constructor_refuses_cpu():
@@ -54,12 +99,25 @@ def test_kernel_matches_reference_golden(tag):
     ref = c['dist']
     assert out.shape == ref.shape
     assert ((out - ref).abs() <= 2e-6 * ref.abs()).all(), ((out - ref).abs() / ref.abs()).max()
-    # with its own host-built grids: same result wherever the nearest-texel choice agrees (a borderline coordinate may pick
-    # the neighbouring texel when a grid value differs in the last bit)
+    # analytic kernel (no grids).  Its sampling coordinates agree with the reference's tabulated grids to a few fp32 ulps of
+    # the normalised coordinate (3.6e-7, checked on the CPU above; the face frames are exact here while the reference's fp32
+    # Rodrigues matrices carry cos(pi/2) ~ 4e-8 residues), i.e. ~1e-5-pixel shifts of the bilinear taps.  On smooth depth
+    # that is a 1e-6 effect; the 1e8 "invalid depth" markers of the golden input (2 % of the pixels) amplify it to
+    # ~shift / weight wherever a tap touches one.  Measured on the CPU restatement of the same closed forms: 94-99 % of the
+    # golden pixels within 2e-6, 99.96 % within 1e-4, all within 1e-3; marker-free input: all within 1e-5.
     m2 = ERPDepth2Dist(c['s'], hw, 'cuda')
     out2 = m2(c['depth'].cuda()).cpu()
-    frac = ((out2 - ref).abs() <= 2e-6 * ref.abs()).float().mean().item()
-    assert frac >= 0.995, frac
+    rel = (out2 - ref).abs() / ref.abs()
+    print(f'analytic kernel vs reference golden [{tag}]: within 2e-6 {(rel <= 2e-6).float().mean().item():.4%}, '
+          f'within 1e-4 {(rel <= 1e-4).float().mean().item():.4%}, max {rel.max().item():.2e}')
+    assert (rel <= 1e-4).float().mean().item() >= 0.995
+    assert (rel <= 2e-3).float().mean().item() >= 0.995      # the rest: texel-boundary ties
+    smooth = c['depth'].clone()
+    smooth[smooth > 1e6] = 2.0
+    ref_s = ERPDepth2Dist(c['s'], hw, 'cuda', grids=(c['c2e'], c['coor'], c['rays']))(smooth.cuda()).cpu()
+    rel_s = (m2(smooth.cuda()).cpu() - ref_s).abs() / ref_s.abs()
+    print(f'  marker-free depth: within 1e-5 {(rel_s <= 1e-5).float().mean().item():.4%}, max {rel_s.max().item():.2e}')
+    assert (rel_s <= 1e-5).float().mean().item() >= 0.995
 
 
 @pytest.mark.gpu
@@ -69,11 +127,26 @@ def test_kernel_matches_oracle_other_size():
     s, hw = 48, (56, 120)
     m = ERPDepth2Dist(s, hw, 'cuda')
     g = torch.Generator().manual_seed(3)
+    c2e, coor, rays = _closed_form_grids(s, hw)
+    # smooth depth: the analytic kernel and the oracle fed with the tabulated closed forms agree to 1e-5 (coordinates agree
+    # to a few fp32 ulps = ~1e-5 pixel; texel-boundary ties < 0.5 %)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, hw[0]), torch.linspace(0, 1, hw[1]), indexing='ij')
+    smooth = 2.0 + torch.sin(5 * xx) * torch.cos(3 * yy)
+    rel = (m(smooth.cuda()).cpu() - erp_depth2dist(smooth, c2e, coor, rays, s)).abs() / erp_depth2dist(smooth, c2e, coor, rays, s).abs()
+    print(f'smooth depth: within 1e-5 {(rel <= 1e-5).float().mean().item():.4%}, max {rel.max().item():.2e}')
+    assert (rel <= 1e-5).float().mean().item() >= 0.995
+    # white-noise depth (gradient ~4 per pixel) with 5 % invalid markers (1e8): the ~1e-5-pixel coordinate noise shows up as
+    # ~2e-5 relative on the noise and as shift / weight next to a marker -- held to 1e-3; the grid-fed kernel on the same
+    # tabulated grids has no coordinate noise and is held to 2e-6 everywhere
     depth = 0.5 + 4 * torch.rand(*hw, generator=g)
     depth[torch.rand(*hw, generator=g) < 0.05] = 1e8
     out = m(depth.cuda()).cpu()
-    ref = erp_depth2dist(depth, m.c2e_grid.cpu(), m.face_coor.cpu(), m.face_rays.cpu(), s)
-    assert ((out - ref).abs() <= 2e-6 * ref.abs()).all()
+    ref = erp_depth2dist(depth, c2e, coor, rays, s)
+    rel = (out - ref).abs() / ref.abs()
+    print(f'noisy depth + markers: within 2e-6 {(rel <= 2e-6).float().mean().item():.4%}, within 1e-3 {(rel <= 1e-3).float().mean().item():.4%}')
+    assert (rel <= 1e-3).float().mean().item() >= 0.99
+    out2 = ERPDepth2Dist(s, hw, 'cuda', grids=(c2e, coor, rays))(depth.cuda()).cpu()
+    assert ((out2 - ref).abs() <= 2e-6 * ref.abs()).all()
 
 
 @pytest.mark.gpu

@@ -152,3 +152,48 @@ def test_backward_linearity_and_accumulation_at_bench_size():
         tol = 2e-3 if name.startswith('w') else 1e-4        # weight gradients: single-pass TF32 contraction over points
         assert (2 * a - b).abs().max().item() <= tol * 2 * s, name
         assert (2 * a - c).abs().max().item() <= tol * 2 * s, name
+
+
+@pytest.mark.parametrize('n_rays,n_samples_d', [(1, 32), (7, 32), (301, 32), (96, 117), (4096, 117)])
+def test_backward_q_kernel_matches_round1_kernel(tmp_path, n_rays, n_samples_d):
+    """The 32-warp TMA-fed backward (backward_q.cu, the product path of nrt_render_bwd) against round 1's kernel
+    (NRT_BWD_IMPL=tc) on the same saved forward, at ragged sizes (partial last tile, tiles spanning several rays) and at the
+    bench shape.  Data gradients (hash table, uncertainty grid) come from the same 3xTF32 chain and may differ only by the
+    summation order of the atomics; the MLP weight gradients are single-pass TF32 contractions over the points in both
+    kernels, in different formulations (geo folded through W2 here).  The switch is read once per process: subprocesses."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = '''
+import sys, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from test_scale_properties import _plan, _rays
+from naruto_b200.field import FieldTensors, RenderBuffers
+cfg, plan, P = _plan(%d, grid_range=0.05)
+B = %d
+o, d, rgb, td = _rays(B, seed=9)
+out = RenderBuffers(B, plan.S, 'cuda', per_sample=True, feat=True)
+stats = plan.new_stats('cuda')
+losses = torch.zeros(8, device='cuda')
+plan.render_fwd_stats(P, o, d, rgb, td, out, stats, u=torch.rand(B, plan.S, generator=torch.Generator().manual_seed(1)).cuda(), losses=losses)
+lg = torch.tensor([5.0, 0.1, 1000.0, 10.0, 0.005], device='cuda')
+G = FieldTensors(*[torch.zeros_like(t) for t in P.as_list()])
+plan.render_bwd(P, o, d, rgb, td, out, stats, lg, G)
+torch.cuda.synchronize()
+torch.save({n: g.cpu() for n, g in zip(('grid', 'w1', 'w2', 'w3', 'w4', 'uncert'), G.as_list())}, sys.argv[1])
+''' % (root, os.path.join(root, 'tests'), n_samples_d, n_rays)
+    res = {}
+    for impl in ('q', 'tc'):
+        f = str(tmp_path / (impl + '.pt'))
+        env = dict(os.environ, NRT_BWD_IMPL=impl)
+        subprocess.run([sys.executable, '-c', code, f], check=True, env=env, timeout=300)
+        res[impl] = torch.load(f)
+    for name in res['q']:
+        a, b = res['q'][name], res['tc'][name]
+        s = b.abs().max().item()
+        assert s > 0 and torch.isfinite(a).all(), name
+        tol = 2e-3 if name.startswith('w') else 2e-5
+        err = (a - b).abs().max().item()
+        print(f'{name}: max |q - tc| = {err:.3e} of scale {s:.3e}')
+        assert err <= tol * s, (name, err, s)
