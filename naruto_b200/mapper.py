@@ -14,9 +14,112 @@ from .field import FieldPlan, FieldTensors, RenderBuffers
 from .parallel import reduce_grads, reduce_stats
 
 
+class FusedState:
+    """Parameters, gradients and Adam moments of the scene model as flat device buffers [grid | w1 | w2 | w3 | w4 | uncert]
+    (the gradient buffer is the all-reduce bucket), plus the device-side step counters.  One FusedState can serve several
+    MappingStep objects (one per batch size); `bind_model` makes a JointEncodingNaruto's nn.Parameters and the state of its
+    torch.optim.Adam optimisers VIEWS of these buffers, so the fused iteration, the autograd path, `query_sdf`,
+    `get_map_volumes`, `save_mesh` and `save_ckpt` / `state_dict` all see one and the same set of numbers."""
+
+    def __init__(self, plan: FieldPlan, device, init: FieldTensors = None):
+        self.plan, self.dev = plan, torch.device(device)
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        ud = plan.uncert_dims
+        self.sizes = [plan.n_grid_floats, 32 * 80, 16 * 32, 32 * 63, 3 * 32, ud[0] * ud[1] * ud[2]]
+        self.shapes = [(plan.n_grid_floats,), (32, 80), (16, 32), (32, 63), (3, 32), tuple(ud)]
+        self.n_grid, self.n_dec, self.n_unc = self.sizes[0], sum(self.sizes[1:5]), self.sizes[5]
+        total = self.total = sum(self.sizes)
+        self.theta = torch.zeros(total, **f32)          # parameters, one flat buffer
+        # gradients, same layout, plus one trailing slot for this rank's part of the smoothness loss: the whole buffer is the
+        # all-reduce bucket, so the loss value is summed across ranks for free
+        self.bucket = torch.zeros(total + 1, **f32)
+        self.grad = self.bucket[:total]
+        self.exp_avg = torch.zeros(total, **f32)
+        self.exp_avg_sq = torch.zeros(total, **f32)
+        self.P, self.G = self.views(self.theta), self.views(self.grad)
+        self.M, self.V = self.views(self.exp_avg), self.views(self.exp_avg_sq)
+        self.map_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.unc_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.n_map_steps = 0        # host mirrors of the two device counters (no synchronisation needed to know them)
+        self.n_unc_steps = 0
+        self._bound = None
+        if init is not None:
+            with torch.no_grad():
+                for dst, src in zip(self.P.as_list(), init.as_list()):
+                    dst.copy_(src.detach().to(self.dev))
+
+    def views(self, buf):
+        out, off = [], 0
+        for n, shp in zip(self.sizes, self.shapes):
+            out.append(buf[off:off + n].view(shp))
+            off += n
+        return FieldTensors(*out)
+
+    def persistent(self):
+        return (self.theta, self.grad, self.exp_avg, self.exp_avg_sq, self.map_step, self.unc_step)
+
+    # ---- one parameter set for every path ---------------------------------------------------------
+    def bind_model(self, model, map_optimizer=None, uncert_optim=None):
+        """Alias `model`'s parameters (embed_fn.params, the four decoder weights, uncert_grid) onto this state: their
+        current values are copied in once, then `param.data` becomes a view of `theta` and `param.grad` a view of the
+        gradient buffer.  If the torch optimisers created by CoSLAMNaruto.create_optimizer / init_uncert_grid_optim
+        (src/slam/coslam/coslam.py:409-419, 240-243) are passed, their Adam state (`exp_avg`, `exp_avg_sq`, `step`) is made to
+        alias / mirror the fused moments too: `optimizer.state_dict()` (save_ckpt) and `optimizer.step()` (the autograd path
+        of first_frame_mapping) stay consistent with fused iterations."""
+        params = model._tensors().as_list()
+        with torch.no_grad():
+            for dst, g, p in zip(self.P.as_list(), self.G.as_list(), params):
+                if p.data_ptr() != dst.data_ptr():
+                    dst.copy_(p.detach().to(self.dev))
+                    p.data = dst
+                p.grad = g
+        self._bound = (model, map_optimizer, uncert_optim)
+        self.sync_optimizers()
+        return self
+
+    def sync_optimizers(self):
+        """Write the fused Adam state into the bound torch optimisers (views for the moments, host step counts)."""
+        if self._bound is None:
+            return
+        model, map_opt, unc_opt = self._bound
+        params = model._tensors().as_list()
+        for opt, idxs, nstep in ((map_opt, range(0, 5), self.n_map_steps), (unc_opt, (5,), self.n_unc_steps)):
+            if opt is None:
+                continue
+            owned = {id(p) for grp in opt.param_groups for p in grp['params']}
+            for i in idxs:
+                p = params[i]
+                if id(p) not in owned:
+                    continue
+                st = opt.state[p]
+                st['exp_avg'], st['exp_avg_sq'] = self.M.as_list()[i], self.V.as_list()[i]
+                st['step'] = torch.tensor(float(nstep))
+
+    def adopt_optimizer_steps(self):
+        """If the bound torch optimisers were stepped outside the fused path (autograd path), take over their step counts."""
+        if self._bound is None:
+            return
+        model, map_opt, unc_opt = self._bound
+        params = model._tensors().as_list()
+
+        def count(opt, i):
+            if opt is None or params[i] not in opt.state or 'step' not in opt.state[params[i]]:
+                return None
+            return int(float(opt.state[params[i]]['step']))
+
+        n = count(map_opt, 0)
+        if n is not None and n != self.n_map_steps:
+            self.n_map_steps = n
+            self.map_step.fill_(n)
+        n = count(unc_opt, 5)
+        if n is not None and n != self.n_unc_steps:
+            self.n_unc_steps = n
+            self.unc_step.fill_(n)
+
+
 class MappingStep:
     def __init__(self, plan: FieldPlan, cfg: dict, n_rays: int, device, init: FieldTensors = None, process_group=None,
-                 use_graph: bool = True, smooth: bool = True):
+                 use_graph: bool = True, smooth: bool = True, state: FusedState = None):
         self.plan, self.cfg, self.B, self.dev = plan, cfg, int(n_rays), torch.device(device)
         self.pg = process_group
         self.rank = torch.distributed.get_rank(process_group) if process_group is not None else 0
@@ -31,31 +134,11 @@ class MappingStep:
         self.smooth_w, self.smooth_n = float(t['smooth_weight']), int(t['smooth_pts'])
         self.smooth_vox, self.smooth_margin = float(t['smooth_vox']), float(t['smooth_margin'])
         f32 = dict(dtype=torch.float32, device=self.dev)
-        ud = plan.uncert_dims
-        sizes = [plan.n_grid_floats, 32 * 80, 16 * 32, 32 * 63, 3 * 32, ud[0] * ud[1] * ud[2]]
-        shapes = [(plan.n_grid_floats,), (32, 80), (16, 32), (32, 63), (3, 32), tuple(ud)]
-        self.n_grid, self.n_dec, self.n_unc = sizes[0], sum(sizes[1:5]), sizes[5]
-        total = sum(sizes)
-        self.theta = torch.zeros(total, **f32)          # parameters, one flat buffer
-        # gradients, same layout, plus one trailing slot for this rank's part of the smoothness loss: the whole buffer is the
-        # all-reduce bucket, so the loss value is summed across ranks for free
-        self.bucket = torch.zeros(total + 1, **f32)
-        self.grad = self.bucket[:total]
-        self.exp_avg = torch.zeros(total, **f32)
-        self.exp_avg_sq = torch.zeros(total, **f32)
-
-        def views(buf):
-            out, off = [], 0
-            for n, shp in zip(sizes, shapes):
-                out.append(buf[off:off + n].view(shp))
-                off += n
-            return FieldTensors(*out)
-
-        self.P, self.G = views(self.theta), views(self.grad)
-        if init is not None:
-            with torch.no_grad():
-                for dst, src in zip(self.P.as_list(), init.as_list()):
-                    dst.copy_(src.detach().to(self.dev))
+        self.state = st = state if state is not None else FusedState(plan, device, init=init)
+        self.n_grid, self.n_dec, self.n_unc = st.n_grid, st.n_dec, st.n_unc
+        total = st.total
+        self.theta, self.bucket, self.grad, self.exp_avg, self.exp_avg_sq = st.theta, st.bucket, st.grad, st.exp_avg, st.exp_avg_sq
+        self.P, self.G = st.P, st.G
         # static buffers (graph inputs / outputs)
         B = self.B
         self.inbuf = torch.zeros(10 * B, **f32)         # packed [o | d | rgb | depth]: one H2D copy per iteration
@@ -73,8 +156,7 @@ class MappingStep:
                                        t.get('uncert_weight', 0.0)], **f32)
         self.ws_bwd = torch.empty(plan.lib.nrt_render_bwd_workspace(plan.h, self.B) // 4, **f32)
         self.ws_smooth = plan.smooth_workspace(self.smooth_n, self.dev)
-        self.map_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
-        self.unc_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.map_step, self.unc_step = st.map_step, st.unc_step
         self.it = 0
         self.use_graph = use_graph
         self.external_random = False     # test hook: keep caller-written self.u / self.rand6 instead of drawing
@@ -87,9 +169,10 @@ class MappingStep:
         self.launches_per_iter = {False: 0, True: 0}
 
     # -------------------------------------------------------------------------------------------
-    def _body(self, with_uncert_step: bool):
+    def _body(self, with_uncert_step: bool, smooth: bool = None):
         """The launches of one iteration on the current stream.  Returns how many kernels of ours it launched."""
         p, n = self.plan, 0
+        smooth = self.smooth_on if smooth is None else (bool(smooth) and self.smooth_w > 0)
         fused_losses = self.losses if self.world == 1 else None      # one shard: the render kernel's last CTA finalizes the losses
         if self.external_random:                            # test hook: caller-written self.u / self.rand6 (the reference's draws)
             p.counter_add(self.map_step, 1); n += 1
@@ -98,15 +181,15 @@ class MappingStep:
         else:
             # the reference's torch.rand(z_vals.shape), torch.rand(3), torch.rand((1,1,1,3)) draws, made on the device from Philox
             # keyed by (seed, step counter): nothing host-side changes between graph replays
-            p.step_begin(self.map_step, self.base_seed, self.rand6 if self.smooth_on else None); n += 1
+            p.step_begin(self.map_step, self.base_seed, self.rand6 if smooth else None); n += 1
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=None,
                                seed=self.seed, seed_step=self.map_step, losses=fused_losses); n += 1
         if fused_losses is None:                            # N > 1: the losses are ratios of GLOBAL sums
             reduce_stats(self.stats, self.pg)
             p.loss_finalize(self.stats, self.losses); n += 1
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,
-                     self.G, workspace=self.ws_bwd); n += 2
-        if self.smooth_on:                                  # ray-independent term: every rank takes one slab of the lattice
+                     self.G, workspace=self.ws_bwd); n += 3     # composite_bwd, decode_bwd_q, wgrad_reduce
+        if smooth:                                          # ray-independent term: every rank takes one slab of the lattice
             p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
                              self.smooth_loss, self.G.grid, self.ws_smooth, part=self.rank, n_parts=self.world); n += 2
         reduce_grads(self.bucket, self.pg)
@@ -125,24 +208,26 @@ class MappingStep:
                         zero_grad=True, step_dev=self.unc_step); n += 1
         return n
 
-    def _graph(self, with_uncert_step):
-        if with_uncert_step not in self._graphs:
+    def _graph(self, with_uncert_step, smooth=None):
+        smooth = self.smooth_on if smooth is None else (bool(smooth) and self.smooth_w > 0)
+        key = (bool(with_uncert_step), smooth)
+        if key not in self._graphs:
             # warm-up outside capture (lazy attribute/module init inside the library and torch RNG)
             side = torch.cuda.Stream(device=self.dev)
-            saved = [b.clone() for b in (self.theta, self.grad, self.exp_avg, self.exp_avg_sq, self.map_step, self.unc_step)]
+            saved = [b.clone() for b in self.state.persistent()]
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._body(with_uncert_step)
+                self._body(with_uncert_step, smooth)
             torch.cuda.current_stream().wait_stream(side)
-            for b, s in zip((self.theta, self.grad, self.exp_avg, self.exp_avg_sq, self.map_step, self.unc_step), saved):
+            for b, s in zip(self.state.persistent(), saved):
                 b.copy_(s)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.launches_per_iter[with_uncert_step] = self._body(with_uncert_step)
-            for b, s in zip((self.theta, self.grad, self.exp_avg, self.exp_avg_sq, self.map_step, self.unc_step), saved):
+                self.launches_per_iter[bool(with_uncert_step)] = self._body(with_uncert_step, smooth)
+            for b, s in zip(self.state.persistent(), saved):
                 b.copy_(s)
-            self._graphs[with_uncert_step] = g
-        return self._graphs[with_uncert_step]
+            self._graphs[key] = g
+        return self._graphs[key]
 
     # -------------------------------------------------------------------------------------------
     def release_graphs(self):
@@ -161,17 +246,34 @@ class MappingStep:
         """One packed [10*B] host (pinned) or device buffer, see SyntheticFrame.sample_packed."""
         self.inbuf.copy_(buf, non_blocking=True)
 
-    def step(self, rays_o=None, rays_d=None, target_rgb=None, target_d=None):
-        """One mapping iteration.  Returns the device tensor of the five losses (no host sync)."""
+    def step(self, rays_o=None, rays_d=None, target_rgb=None, target_d=None, with_uncert_step=None, smooth=None):
+        """One mapping iteration.  Returns the device tensor of the five losses (no host sync).
+        with_uncert_step: step + zero the uncertainty-grid Adam group in this iteration (default: every 5th iteration of this
+        object, src/slam/coslam/coslam.py:397-399; a caller that follows global_BA's own loop index passes it explicitly);
+        smooth: include the smoothness term (default: as constructed; first_frame_mapping runs without it)."""
         if rays_o is not None:
             self.load_rays(rays_o, rays_d, target_rgb, target_d)
-        with_unc = (self.it + 1) % 5 == 0
+        with_unc = (self.it + 1) % 5 == 0 if with_uncert_step is None else bool(with_uncert_step)
         if self.use_graph:
-            self._graph(with_unc).replay()
+            self._graph(with_unc, smooth).replay()
         else:
-            self.launches_per_iter[with_unc] = self._body(with_unc)
+            self.launches_per_iter[with_unc] = self._body(with_unc, smooth)
         self.it += 1
+        self.state.n_map_steps += 1
+        self.state.n_unc_steps += 1 if with_unc else 0
         return self.losses
+
+    def uncert_step(self):
+        """A stand-alone uncertainty-grid Adam step + zero_grad (first_frame_mapping steps it once, after all its iterations:
+        src/slam/coslam/coslam.py:217-218)."""
+        p, o = self.plan, self.n_grid + self.n_dec
+        p.counter_add(self.unc_step, 1)
+        p.adam_step(self.theta[o:], self.grad[o:], self.exp_avg[o:], self.exp_avg_sq[o:], 0, 1.0, 0.9, 0.999, 1e-8, 0.0,
+                    zero_grad=True, step_dev=self.unc_step)
+        self.state.n_unc_steps += 1
+
+    def zero_uncert_grad(self):
+        self.grad[self.n_grid + self.n_dec:].zero_()
 
     def total_loss(self):
         """get_loss_from_ret's scalar (host sync)."""

@@ -127,31 +127,56 @@ class _DecodeFn(torch.autograd.Function):
         return (None, None) + tuple(G.as_list())
 
 
+class _TrainBuffers:
+    """Persistent per-batch-size buffers of the training forward (render outputs incl. the saved features / masks, loss
+    statistics, backward workspace, one flat gradient buffer): allocated once per batch size and reused, so an iteration
+    through the autograd path allocates nothing large (round 1 zero-filled a fresh 67 MB feature buffer and six gradient
+    tensors per call).  `version` guards against a second forward overwriting what a pending backward still needs."""
+
+    def __init__(self, plan, B, device, sizes, shapes):
+        self.out = RenderBuffers(B, plan.S, device, per_sample=True, feat=True)
+        self.stats = plan.new_stats(device)
+        self.ws = torch.empty(plan.lib.nrt_render_bwd_workspace(plan.h, B) // 4, dtype=torch.float32, device=device)
+        self.sizes, self.shapes = sizes, shapes
+        self.version = 0
+
+    def new_grads(self, device):
+        flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=device)     # one memset; autograd owns the result
+        out, off = [], 0
+        for n, shp in zip(self.sizes, self.shapes):
+            out.append(flat[off:off + n].view(shp))
+            off += n
+        return out
+
+
 class _RenderLossFn(torch.autograd.Function):
-    """forward(): fused render + loss statistics; backward(): the three backward kernels."""
+    """forward(): ONE launch -- fused render + loss statistics + finalized losses (nrt_render_fwd_stats);
+    backward(): nrt_render_bwd (composite_bwd, the TMA-fed MLP-backward / scatter kernel, the weight-gradient reduction)."""
 
     @staticmethod
-    def forward(ctx, plan, rays_o, rays_d, target_rgb, target_d, u, seed, grid, w1, w2, w3, w4, uncert):
+    def forward(ctx, plan, bufs, rays_o, rays_d, target_rgb, target_d, u, seed, grid, w1, w2, w3, w4, uncert):
         P = FieldTensors(grid, w1, w2, w3, w4, uncert)
-        B = rays_o.shape[0]
-        out = RenderBuffers(B, plan.S, rays_o.device, per_sample=True, feat=True)
-        plan.render_fwd(P, rays_o, rays_d, target_d, out, u=u, seed=seed)
-        stats = plan.new_stats(rays_o.device)
+        bufs.version += 1
         losses = torch.empty(L.N_LOSS, dtype=torch.float32, device=rays_o.device)
-        plan.loss_partial(out, target_rgb, target_d, stats)
-        plan.loss_finalize(stats, losses)
-        ctx.plan, ctx.out, ctx.stats = plan, out, stats
+        plan.render_fwd_stats(P, rays_o, rays_d, target_rgb, target_d, bufs.out, bufs.stats, u=u, seed=seed, losses=losses)
+        ctx.plan, ctx.bufs, ctx.version = plan, bufs, bufs.version
         ctx.save_for_backward(rays_o, rays_d, target_rgb, target_d, grid, w1, w2, w3, w4, uncert)
-        ctx.mark_non_differentiable(out.rgb, out.depth)
-        return losses, out.rgb, out.depth
+        rgb, depth = bufs.out.rgb.clone(), bufs.out.depth.clone()       # the caller keeps these; the buffers are reused
+        ctx.mark_non_differentiable(rgb, depth)
+        return losses, rgb, depth
 
     @staticmethod
     def backward(ctx, dlosses, _drgb, _ddepth):
         rays_o, rays_d, target_rgb, target_d, *params = ctx.saved_tensors
+        bufs = ctx.bufs
+        if bufs.version != ctx.version:
+            raise L.NrtError('naruto_b200: backward() of a training forward whose saved activations were overwritten by a later '
+                             'forward() of the same batch size (call backward before the next forward, as the reference\'s '
+                             'mapping loop does)')
         P = FieldTensors(*params)
-        G = FieldTensors(*[torch.zeros_like(t) for t in params])
-        ctx.plan.render_bwd(P, rays_o, rays_d, target_rgb, target_d, ctx.out, ctx.stats, dlosses.contiguous(), G)
-        return (None,) * 7 + tuple(G.as_list())
+        G = FieldTensors(*bufs.new_grads(rays_o.device))
+        ctx.plan.render_bwd(P, rays_o, rays_d, target_rgb, target_d, bufs.out, bufs.stats, dlosses.contiguous(), G, workspace=bufs.ws)
+        return (None,) * 8 + tuple(G.as_list())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -175,6 +200,7 @@ class JointEncodingNaruto(nn.Module):
         self.sdf_net = self.decoder.sdf_net
         self.act_uncertainty = nn.Softplus()
         self._seed = 0
+        self._train_bufs = {}                  # (B, S, device) -> _TrainBuffers of the autograd training path
         self.strict_uncert_assert = False      # True => reproduce `assert uncert_map.min() > 0` (costs a host sync)
 
     # ---- parameters ----------------------------------------------------------------------------
@@ -184,7 +210,9 @@ class JointEncodingNaruto(nn.Module):
         if dims != self.plan.uncert_dims:
             self.plan = FieldPlan(self.config, self.bounding_box, uncert_voxel=voxel_size)
             self.embed_fn.plan = self.embedpos_fn.plan = self.plan
-        self.uncert_grid = nn.Parameter(torch.ones(dims, device='cuda').float() * 3)
+        # the reference hard-codes device="cuda" here (its model always lives there); follow the model instead so that the class
+        # also constructs where there is no GPU (host-side tests of the Mapper wiring)
+        self.uncert_grid = nn.Parameter(torch.ones(dims, device=self.embed_fn.params.device).float() * 3)
         self.cache_uncert = np.zeros(dims, dtype=np.float32)
         return self.uncert_grid
 
@@ -308,8 +336,16 @@ class JointEncodingNaruto(nn.Module):
             raise L.NrtError('naruto_b200: rays_o / rays_d require grad, but the fused renderer has no pose gradient '
                              '(NARUTO maps with fixed poses); pass detached rays')
         f = lambda t: t.detach().float().contiguous()
-        losses, rgb, depth = _RenderLossFn.apply(self.plan, f(rays_o), f(rays_d), f(target_rgb), f(target_d), u,
-                                                 self._next_seed(), *self._tensors().as_list())
+        P = self._tensors()
+        B = rays_o.shape[0]
+        key = (B, self.plan.S, rays_o.device)
+        if key not in self._train_bufs:
+            if len(self._train_bufs) >= 4:
+                self._train_bufs.pop(next(iter(self._train_bufs)))
+            tl = P.as_list()
+            self._train_bufs[key] = _TrainBuffers(self.plan, B, rays_o.device, [t.numel() for t in tl], [tuple(t.shape) for t in tl])
+        losses, rgb, depth = _RenderLossFn.apply(self.plan, self._train_bufs[key], f(rays_o), f(rays_d), f(target_rgb),
+                                                 f(target_d), u, self._next_seed(), *P.as_list())
         if self.strict_uncert_assert:
             assert losses[L.LOSS_UNCERT_MIN].item() > 0
         return {'rgb': rgb, 'depth': depth, 'rgb_loss': losses[L.LOSS_RGB], 'depth_loss': losses[L.LOSS_DEPTH],

@@ -1,8 +1,10 @@
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2i_tests.log 2>&1; tail -5 gpurun_out/r2i_tests.log
-P="python tools/probe_bwd.py"
-PROBE_WARPS=1 NRT_BWD_DEBUG=8 $P 4096 117 > gpurun_out/r2i_probe.log 2>&1
-NRT_BWD_DEBUG=24 $P 4096 117 >> gpurun_out/r2i_probe.log 2>&1
-NRT_BWD_DEBUG=8 $P 32768 117 >> gpurun_out/r2i_probe.log 2>&1
-NRT_BWD_DEBUG=8 $P 2148 32 >> gpurun_out/r2i_probe.log 2>&1
-NRT_BWD_IMPL=tc $P 4096 117 >> gpurun_out/r2i_probe.log 2>&1
-grep -v "mlp \|scat " gpurun_out/r2i_probe.log; grep " 0 scat\| 8 scat\|15 scat\|16 mlp\|17 mlp" gpurun_out/r2i_probe.log | head -10
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2j_tests.log 2>&1; tail -8 gpurun_out/r2j_tests.log
+timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/r2j_bench.json 2> gpurun_out/r2j_bench.err; echo rc=$?
+tail -3 gpurun_out/r2j_bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2j_bench.json'))
+print(d['value'], d['ms_per_step'], d['e2e'], d['kernels'], d['roofline']['frac'])
+print('sweep', d.get('sweep')); print('dropin', d.get('e2e_dropin')); print('torch', d.get('torch_gpu_baseline')); print('cpu', d.get('cpu_baseline'))
+print('configs', json.dumps(d.get('configs'), indent=1))
+PY
