@@ -253,6 +253,47 @@ int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream);
  * tp/coslam.py:252-258) from Philox keyed by (seed, new counter value) -> rand6_dev (dev fp32 [6], optional). */
 int nrt_step_begin(int32_t* counter_dev, int32_t delta, uint64_t seed, float* rand6_dev, void* stream);
 
+/* ---- data-parallel exchanges over NVLink peer memory (no NCCL on the iteration's path) ----------------------------
+ * Ray-sharded data parallelism exchanges the loss statistics before the backward pass and the gradient bucket
+ * before Adam.  With these two entry points both exchanges happen inside the kernels that consume the data, over buffers that
+ * every rank has mapped from every other rank (symmetric memory; the host side sets this up once, e.g. with
+ * torch.distributed._symmetric_memory).  All pointer tables are HOST arrays of DEVICE pointers indexed by rank.
+ *   bucket[r]     dev fp32 [pad4(total) + 4]  flat gradient [grid | w1 | w2 | w3 | w4 | uncert], the smoothness-loss slot behind it
+ *   theta[r]      dev fp32 [pad4(total)]      flat parameters, same layout
+ *   stats_pad[r]  dev fp64 [world * NRT_N_STATS]
+ *   flags[r]      dev u32  [3 * 8], zero-filled once
+ * Every rank must make the same sequence of calls (one nrt_stats_exchange, then one nrt_adam_step_peers per iteration). */
+typedef struct NrtPeerTable {
+  int32_t world, rank;        /* world <= 8 */
+  float* bucket[8];
+  float* theta[8];
+  double* stats_pad[8];
+  uint32_t* flags[8];
+} NrtPeerTable;
+
+/* One Adam parameter group of the flat vector: floats [begin, end), begin a multiple of 4 and every buffer padded to a whole
+ * number of float4s behind `end` (padding gradients stay zero), torch.optim.Adam hyper-parameters, the
+ * group's device-side 1-based step counter (already advanced), enabled = 0 skips the group (its gradient keeps accumulating
+ * locally, like the every-5th uncertainty-grid step of src/slam/coslam/coslam.py:397-399). */
+typedef struct NrtAdamGroup {
+  int64_t begin, end;
+  float lr, beta1, beta2, eps, weight_decay;
+  const int32_t* step_dev;
+  int32_t enabled;
+} NrtAdamGroup;
+
+/* all-reduce of the loss statistics + nrt_loss_finalize in one launch: stats (dev, this rank's sums from
+ * nrt_render_fwd_stats) is overwritten with the global sums, losses as nrt_loss_finalize.  xchg: dev u32 exchange counter of
+ * this rank (zero-filled once; advanced here, read by nrt_adam_step_peers). */
+int nrt_stats_exchange(const NrtPeerTable* peers, double* stats, uint32_t* xchg, float* losses, void* stream);
+/* reduce-scatter + Adam + all-gather in one launch: every rank reduces and steps its 1/world slice of each enabled group
+ * (gradients summed over the ranks in rank order, then cleared on every rank), with its local moments exp_avg / exp_avg_sq
+ * (dev fp32 [total]; only the rank's own slices are maintained), and stores the updated parameters into every rank's theta.
+ * smooth_slot: index of the smoothness-loss slot in bucket (its sum over ranks -> smooth_total, dev fp32 [1], may be NULL).
+ * done_counter: dev u32 scratch, zero-filled once.  Returns after every rank's stores are visible everywhere. */
+int nrt_adam_step_peers(const NrtPeerTable* peers, float* exp_avg, float* exp_avg_sq, const NrtAdamGroup* groups, int32_t n_groups,
+                        int64_t smooth_slot, float* smooth_total, const uint32_t* xchg, uint32_t* done_counter, void* stream);
+
 /* ---- device-resident ray sampling ----------------------------------------------------------------
  * The host half of the mapping iteration on device-resident data.  Index lists are dev int64
  * arrays: either the reference's own `random.sample` draws (parity) or the output of nrt_sample_indices. */

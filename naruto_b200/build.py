@@ -13,7 +13,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libnaruto_b200.so')
 STAMP = os.path.join(HERE, '.build_stamp')
-SOURCES = ['api.cu', 'forward.cu', 'forward_tc.cu', 'forward_ws.cu', 'backward.cu', 'backward_tc.cu', 'backward_q.cu', 'optim.cu', 'sampler.cu', 'erp.cu', 'planner.cu', 'mcubes.cu', 'selftest.cu']
+SOURCES = ['api.cu', 'forward.cu', 'forward_tc.cu', 'forward_ws.cu', 'backward.cu', 'backward_tc.cu', 'backward_q.cu', 'optim.cu', 'peer.cu', 'sampler.cu', 'erp.cu', 'planner.cu', 'mcubes.cu', 'selftest.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '--expt-relaxed-constexpr']
 

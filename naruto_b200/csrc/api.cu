@@ -45,6 +45,9 @@ int launch_goal_aggregate(const float*, const float*, const int*, const float*, 
                           float*, float*, int*, int, cudaStream_t);
 int launch_erp_depth2dist(const float*, int, int, const float*, const float*, const float*, int, float*, int, cudaStream_t);
 int launch_erp_depth2dist_analytic(const float*, int, int, int, const float*, float, float*, int, cudaStream_t);
+int launch_stats_exchange(const NrtPeerTable*, double*, unsigned int*, float*, cudaStream_t);
+int launch_adam_peers(const NrtPeerTable*, float*, float*, const NrtAdamGroup*, int, int64_t, float*, const unsigned int*, unsigned int*, int,
+                      cudaStream_t);
 int launch_camera_rays(int, int, float, float, float, float, float*, cudaStream_t);
 int launch_pack_frame(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
 int launch_valid_depth_count(const float*, int64_t, float, int*, cudaStream_t);
@@ -385,6 +388,30 @@ int nrt_erp_depth2dist_analytic(const float* erp_depth, int32_t H, int32_t W, in
   NRT_REQUIRE((int64_t)H * W == 0 || (erp_depth && erp_dist && W % 4 == 0 && W >= 8 && H >= 2), "erp_depth2dist_analytic arguments");
   return launch_erp_depth2dist_analytic(erp_depth, H, W, skybox_size, face_rot, x_max, erp_dist, nrt_device_sm_count(),
                                         (cudaStream_t)stream);
+}
+
+static int check_peers(const NrtPeerTable* p) {
+  NRT_REQUIRE(p && p->world >= 1 && p->world <= 8 && p->rank >= 0 && p->rank < p->world, "peer table: 1 <= world <= 8, 0 <= rank < world");
+  for (int r = 0; r < p->world; ++r)
+    NRT_REQUIRE(p->bucket[r] && p->theta[r] && p->stats_pad[r] && p->flags[r], "peer table has a null pointer");
+  return NRT_OK;
+}
+
+int nrt_stats_exchange(const NrtPeerTable* peers, double* stats, uint32_t* xchg, float* losses, void* stream) {
+  if (int rc = check_peers(peers)) return rc;
+  NRT_REQUIRE(stats && xchg && losses, "stats_exchange arguments");
+  return launch_stats_exchange(peers, stats, xchg, losses, (cudaStream_t)stream);
+}
+
+int nrt_adam_step_peers(const NrtPeerTable* peers, float* exp_avg, float* exp_avg_sq, const NrtAdamGroup* groups, int32_t n_groups,
+                        int64_t smooth_slot, float* smooth_total, const uint32_t* xchg, uint32_t* done_counter, void* stream) {
+  if (int rc = check_peers(peers)) return rc;
+  NRT_REQUIRE(exp_avg && exp_avg_sq && groups && n_groups >= 1 && n_groups <= 3 && xchg && done_counter, "adam_step_peers arguments");
+  for (int i = 0; i < n_groups; ++i)
+    NRT_REQUIRE(groups[i].begin % 4 == 0 && groups[i].end >= groups[i].begin && (groups[i].step_dev || !groups[i].enabled),
+                "adam group: begin a multiple of 4 floats, step counter on the device");
+  return launch_adam_peers(peers, exp_avg, exp_avg_sq, groups, n_groups, smooth_slot, smooth_total, xchg, done_counter,
+                           nrt_device_sm_count(), (cudaStream_t)stream);
 }
 
 int nrt_step_begin(int32_t* counter_dev, int32_t delta, uint64_t seed, float* rand6_dev, void* stream) {

@@ -7,11 +7,13 @@ Data parallel (SURVEY.md 8e): each rank renders its own shard of the ray batch; 
 all-reduced before the backward pass because every loss is a ratio of global sums, and the flat gradient buffer
 [grid | w1 | w2 | w3 | w4 | uncert] is all-reduced (NCCL over NVLink) before an identical Adam step on every rank.
 """
+import os
+
 import torch
 
 from . import _lib as L
 from .field import FieldPlan, FieldTensors, RenderBuffers
-from .parallel import reduce_grads, reduce_stats
+from .parallel import PeerExchange, reduce_grads, reduce_stats
 
 
 class FusedState:
@@ -21,7 +23,7 @@ class FusedState:
     torch.optim.Adam optimisers VIEWS of these buffers, so the fused iteration, the autograd path, `query_sdf`,
     `get_map_volumes`, `save_mesh` and `save_ckpt` / `state_dict` all see one and the same set of numbers."""
 
-    def __init__(self, plan: FieldPlan, device, init: FieldTensors = None):
+    def __init__(self, plan: FieldPlan, device, init: FieldTensors = None, process_group=None):
         self.plan, self.dev = plan, torch.device(device)
         f32 = dict(dtype=torch.float32, device=self.dev)
         ud = plan.uncert_dims
@@ -29,13 +31,29 @@ class FusedState:
         self.shapes = [(plan.n_grid_floats,), (32, 80), (16, 32), (32, 63), (3, 32), tuple(ud)]
         self.n_grid, self.n_dec, self.n_unc = self.sizes[0], sum(self.sizes[1:5]), self.sizes[5]
         total = self.total = sum(self.sizes)
-        self.theta = torch.zeros(total, **f32)          # parameters, one flat buffer
-        # gradients, same layout, plus one trailing slot for this rank's part of the smoothness loss: the whole buffer is the
-        # all-reduce bucket, so the loss value is summed across ranks for free
-        self.bucket = torch.zeros(total + 1, **f32)
+        # Data parallel: parameters and the gradient bucket live in NVLink-mapped symmetric memory when it is available, and the
+        # two exchanges of the iteration run inside our own kernels (csrc/peer.cu); NRT_DP_IMPL=nccl forces the NCCL all-reduces
+        self.peers = None
+        if process_group is not None and torch.distributed.get_world_size(process_group) > 1 \
+                and os.environ.get('NRT_DP_IMPL', 'peer') != 'nccl' and self.dev.type == 'cuda':
+            try:
+                self.peers = PeerExchange(total, self.dev, process_group)
+            except Exception as e:       # no P2P / symmetric memory on this system: NCCL path
+                import warnings
+                warnings.warn(f'naruto_b200: peer-memory exchange unavailable ({e!r}); using NCCL all-reduces')
+                self.peers = None
+        self.smooth_slot = total
+        pad = (total + 3) // 4 * 4
+        if self.peers is not None:
+            self.theta, self.bucket, self.smooth_slot = self.peers.theta[:total], self.peers.bucket, self.peers.smooth_slot
+        else:
+            self.theta = torch.zeros(total, **f32)          # parameters, one flat buffer
+            # gradients, same layout, plus one trailing slot for this rank's part of the smoothness loss: the whole buffer is the
+            # all-reduce bucket, so the loss value is summed across ranks for free
+            self.bucket = torch.zeros(total + 1, **f32)
         self.grad = self.bucket[:total]
-        self.exp_avg = torch.zeros(total, **f32)
-        self.exp_avg_sq = torch.zeros(total, **f32)
+        self.exp_avg = torch.zeros(pad, **f32)[:total]          # (storage padded to whole float4s for the peer-memory Adam)
+        self.exp_avg_sq = torch.zeros(pad, **f32)[:total]
         self.P, self.G = self.views(self.theta), self.views(self.grad)
         self.M, self.V = self.views(self.exp_avg), self.views(self.exp_avg_sq)
         self.map_step = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -134,7 +152,8 @@ class MappingStep:
         self.smooth_w, self.smooth_n = float(t['smooth_weight']), int(t['smooth_pts'])
         self.smooth_vox, self.smooth_margin = float(t['smooth_vox']), float(t['smooth_margin'])
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.state = st = state if state is not None else FusedState(plan, device, init=init)
+        self.state = st = state if state is not None else FusedState(plan, device, init=init, process_group=process_group)
+        self.peers = st.peers
         self.n_grid, self.n_dec, self.n_unc = st.n_grid, st.n_dec, st.n_unc
         total = st.total
         self.theta, self.bucket, self.grad, self.exp_avg, self.exp_avg_sq = st.theta, st.bucket, st.grad, st.exp_avg, st.exp_avg_sq
@@ -151,7 +170,9 @@ class MappingStep:
         self.rand6 = torch.zeros(6, **f32)
         self.stats = plan.new_stats(self.dev)
         self.losses = torch.zeros(L.N_LOSS, **f32)
-        self.smooth_loss = self.bucket[total:total + 1]
+        self.smooth_loss = self.bucket[st.smooth_slot:st.smooth_slot + 1]
+        # N > 1 with peer memory: the sum of the ranks' slab losses lands here (the bucket slot itself is rank-local then)
+        self.smooth_total = torch.zeros(1, **f32)
         self.loss_grad = torch.tensor([t['rgb_weight'], t['depth_weight'], t['sdf_weight'], t['fs_weight'],
                                        t.get('uncert_weight', 0.0)], **f32)
         self.ws_bwd = torch.empty(plan.lib.nrt_render_bwd_workspace(plan.h, self.B) // 4, **f32)
@@ -185,15 +206,28 @@ class MappingStep:
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=None,
                                seed=self.seed, seed_step=self.map_step, losses=fused_losses); n += 1
         if fused_losses is None:                            # N > 1: the losses are ratios of GLOBAL sums
-            reduce_stats(self.stats, self.pg)
-            p.loss_finalize(self.stats, self.losses); n += 1
+            if self.peers is not None:                      # exchange + finalize in one launch over peer memory
+                self.peers.stats_exchange(self.stats, self.losses); n += 1
+            else:
+                reduce_stats(self.stats, self.pg)
+                p.loss_finalize(self.stats, self.losses); n += 1
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,
                      self.G, workspace=self.ws_bwd); n += 3     # composite_bwd, decode_bwd_q, wgrad_reduce
         if smooth:                                          # ray-independent term: every rank takes one slab of the lattice
             p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
                              self.smooth_loss, self.G.grid, self.ws_smooth, part=self.rank, n_parts=self.world); n += 2
-        reduce_grads(self.bucket, self.pg)
         ng, nd = self.n_grid, self.n_dec
+        if self.peers is not None:
+            # reduce-scatter + Adam (all three groups) + all-gather in ONE launch over peer memory (csrc/peer.cu)
+            if with_uncert_step:
+                p.counter_add(self.unc_step, 1); n += 1
+            self.peers.adam_step(self.exp_avg, self.exp_avg_sq, [
+                (0, ng, self.lr_embed, 0.9, 0.99, 1e-15, 0.0, self.map_step, True),
+                (ng, ng + nd, self.lr_decoder, 0.9, 0.99, 1e-8, 1e-6, self.map_step, True),
+                (ng + nd, ng + nd + self.n_unc, 1.0, 0.9, 0.999, 1e-8, 0.0, self.unc_step, bool(with_uncert_step))],
+                self.smooth_total if smooth else None); n += 1
+            return n
+        reduce_grads(self.bucket, self.pg)
         # create_optimizer (src/slam/coslam/coslam.py:409-419): decoder group wd=1e-6, grid group eps=1e-15, betas (0.9,0.99)
         p.adam_step(self.theta[:ng], self.grad[:ng], self.exp_avg[:ng], self.exp_avg_sq[:ng], 0, self.lr_embed, 0.9, 0.99,
                     1e-15, 0.0, zero_grad=True, step_dev=self.map_step); n += 1
@@ -267,6 +301,8 @@ class MappingStep:
         """A stand-alone uncertainty-grid Adam step + zero_grad (first_frame_mapping steps it once, after all its iterations:
         src/slam/coslam/coslam.py:217-218)."""
         p, o = self.plan, self.n_grid + self.n_dec
+        if self.world > 1:            # stand-alone step outside the iteration: plain all-reduce of the accumulated slice
+            torch.distributed.all_reduce(self.grad[o:], group=self.pg)
         p.counter_add(self.unc_step, 1)
         p.adam_step(self.theta[o:], self.grad[o:], self.exp_avg[o:], self.exp_avg_sq[o:], 0, 1.0, 0.9, 0.999, 1e-8, 0.0,
                     zero_grad=True, step_dev=self.unc_step)
@@ -281,5 +317,5 @@ class MappingStep:
         w = self.loss_grad.double().cpu()
         tot = float((l * w).sum())
         if self.smooth_on:
-            tot += self.smooth_w * float(self.smooth_loss.item())
+            tot += self.smooth_w * float((self.smooth_total if self.peers is not None else self.smooth_loss).item())
         return tot

@@ -1,10 +1,9 @@
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2j_tests.log 2>&1; tail -8 gpurun_out/r2j_tests.log
-timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/r2j_bench.json 2> gpurun_out/r2j_bench.err; echo rc=$?
-tail -3 gpurun_out/r2j_bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/r2j_bench.json'))
-print(d['value'], d['ms_per_step'], d['e2e'], d['kernels'], d['roofline']['frac'])
-print('sweep', d.get('sweep')); print('dropin', d.get('e2e_dropin')); print('torch', d.get('torch_gpu_baseline')); print('cpu', d.get('cpu_baseline'))
-print('configs', json.dumps(d.get('configs'), indent=1))
-PY
+for impl in peer; do
+NRT_DP_IMPL=$impl timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 30 --warmup 5 > gpurun_out/r2m_bench8_$impl.json 2> gpurun_out/r2m_bench8_$impl.err; echo rc=$?
+grep -v "^\[W\|^$\|\*\*\*\|Warning\|symm.enable" gpurun_out/r2m_bench8_$impl.err | tail -5
+python -c "
+import json;d=json.load(open('gpurun_out/r2m_bench8_$impl.json'));print('$impl',d['value'],d['ms_per_step'],d['e2e']['ms_per_step'],d['gpu_launches']); print({k:(v['ms_per_step'],v['rays_per_s']) for k,v in d['configs'].items()})"
+done
+NRT_DP_IMPL=peer timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 30 --warmup 5 --no-side-configs > gpurun_out/r2m_bench4_peer.json 2> gpurun_out/r2m_bench4_peer.err; echo rc=$?
+python -c "
+import json;d=json.load(open('gpurun_out/r2m_bench4_peer.json'));print('peer4',d['value'],d['ms_per_step'],d['e2e']['ms_per_step'])"
