@@ -132,6 +132,18 @@ def build_reference_slam(model_cls=None, tmp_dir=None, active_ray=True):
         if model_cls is not None:
             coslam_mod.JointEncoding = model_cls
         sink = io.StringIO()
-        with contextlib.redirect_stdout(sink):
-            slam = coslam_mod.CoSLAMNaruto(main_cfg, InfoPrinter('test'))
+        # the reference's get_uncert_grid hard-codes device="cuda" (src/slam/coslam/model/scene_rep.py:54): drop the argument
+        # while the object is being constructed on the CPU
+        real_ones = torch.ones
+
+        def ones_here(*a, **k):
+            k.pop('device', None)
+            return real_ones(*a, **k)
+
+        torch.ones = ones_here
+        try:
+            with contextlib.redirect_stdout(sink):
+                slam = coslam_mod.CoSLAMNaruto(main_cfg, InfoPrinter('test'))
+        finally:
+            torch.ones = real_ones
     return slam, coslam_mod

@@ -48,13 +48,14 @@ def close(a, b, rel=REL, name='', scale=None):
     assert err <= rel * max(s, 1e-30), f'{name}: max abs err {err:.3e} vs scale {s:.3e} (rel {err / max(s, 1e-30):.2e})'
 
 
-def rays_close(a, b, name, rel=REL, frac=0.995, hard=1e-2):
+def rays_close(a, b, name, rel=REL, frac=0.999, hard=1e-2):     # measured on B200: 100 % of the rays of every golden case, worst 3e-7
     a = a.detach().float().cpu().numpy()
     b = np.asarray(b)
     d = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
     if d.ndim > 1:
         d = d.max(axis=tuple(range(1, d.ndim)))
     ok = (d <= rel).mean()
+    print(f'{name}: {ok * 100:.3f}% of {d.size} rays within {rel} of the reference (worst {d.max():.2e})')
     assert ok >= frac, f'{name}: only {ok * 100:.2f}% of rays within {rel}'
     assert d.max() <= hard, f'{name}: worst ray off by {d.max():.3e}'
 
@@ -105,7 +106,7 @@ def test_render_rays_vs_golden(spec, dev, tag, perturb):
     close(r2['z_vals'], g['z_vals'], 1e-6, 'in-kernel z_vals', scale=5.0)
     close(r2['raw'], g['raw'], 5e-4, 'raw (kernel z)')
     for k in ('rgb', 'depth', 'uncert_map'):
-        rays_close(r2[k], g[k], k + ' (kernel z)', frac=0.98)
+        rays_close(r2[k], g[k], k + ' (kernel z)', frac=0.999)
     # forward() in eval mode returns the same dict
     r3 = m(o, d, torch.zeros_like(o), td, u=t(g['u'], dev) if perturb else None)
     assert torch.equal(r3['depth'], r2['depth'])
@@ -152,8 +153,8 @@ def test_train_forward_backward_vs_golden(spec, dev, tag):
     assert ret['psnr'].shape == (1,) and ret['rgb_loss'].dim() == 0
     for k in ('rgb_loss', 'depth_loss', 'sdf_loss', 'fs_loss', 'uncert_loss', 'psnr'):
         close(ret[k], g[k], 2e-4, k)
-    rays_close(ret['rgb'], g['rgb'], 'rgb', frac=0.98)
-    rays_close(ret['depth'], g['depth'], 'depth', frac=0.98)
+    rays_close(ret['rgb'], g['rgb'], 'rgb', frac=0.999)
+    rays_close(ret['depth'], g['depth'], 'depth', frac=0.999)
     loss = (spec.rgb_weight * ret['rgb_loss'] + spec.depth_weight * ret['depth_loss'] + spec.sdf_weight * ret['sdf_loss']
             + spec.fs_weight * ret['fs_loss'] + spec.uncert_weight * ret['uncert_loss'])
     close(loss, g['loss'], 2e-4, 'loss')
@@ -308,3 +309,37 @@ def test_other_baseline_configs_vs_oracle(dev, name, bound, hash_size, n_samples
     close(m.decoder.color_net.model[2].weight.grad, Pg.w4.grad, 2e-3, name + ' w4 grad')
     close(m.embed_fn.params.grad, Pg.grid.grad, 2e-3, name + ' grid grad')
     close(m.uncert_grid.grad, Pg.uncert_grid.grad, 2e-3, name + ' uncert grad')
+
+
+def test_train_matches_oracle_at_the_bench_shape(spec, dev):
+    """4096 rays x 128 samples -- the shape bench.py times -- against the oracle on the CPU (about 2 s on 16 cores): losses,
+    per-ray outputs (the fraction of rays outside 1e-4 is PRINTED, not budgeted loosely: a sample whose truncation mask flips
+    moves its ray), and every parameter gradient."""
+    sp = no.office0_spec(n_samples_d=117)
+    P = no.init_params(sp, seed=11, grid_range=0.3, uncert_jitter=1.0)
+    from oracle.make_golden import synth_rays
+    B = 4096
+    o, d, rgb, td = synth_rays(sp, B, seed=21)
+    u = torch.rand(B, sp.n_samples, generator=torch.Generator().manual_seed(4))
+    Pg = P.clone(requires_grad=True)
+    ret_o = no.forward_train(o, d, rgb, td, Pg, sp, u=u)
+    no.total_loss(ret_o, sp).backward()
+    m = make_model(sp, P, dev, n_samples_d=117).train()
+    ret = m.forward(o.to(dev), d.to(dev), rgb.to(dev), td.to(dev), u=u.to(dev))
+    for k in ('rgb_loss', 'depth_loss', 'sdf_loss', 'fs_loss', 'uncert_loss'):
+        close(ret[k], ret_o[k], 2e-4, k)
+    for k in ('rgb', 'depth'):
+        a, b = ret[k].detach().cpu(), ret_o[k].detach()
+        bad = ((a - b).abs() > 1e-4 * (1.0 + b.abs())).reshape(B, -1).any(dim=1)
+        print(f'bench shape, {k}: {bad.float().mean().item():.4%} of {B} rays differ from the oracle by more than 1e-4 '
+              f'(max abs diff {(a - b).abs().max().item():.2e})')
+        assert bad.float().mean().item() <= 0.005
+    loss = (sp.rgb_weight * ret['rgb_loss'] + sp.depth_weight * ret['depth_loss'] + sp.sdf_weight * ret['sdf_loss']
+            + sp.fs_weight * ret['fs_loss'] + sp.uncert_weight * ret['uncert_loss'])
+    loss.backward()
+    close(m.decoder.sdf_net.model[0].weight.grad, Pg.w1.grad, 2e-3, 'w1 grad')
+    close(m.decoder.sdf_net.model[2].weight.grad, Pg.w2.grad, 2e-3, 'w2 grad')
+    close(m.decoder.color_net.model[0].weight.grad, Pg.w3.grad, 2e-3, 'w3 grad')
+    close(m.decoder.color_net.model[2].weight.grad, Pg.w4.grad, 2e-3, 'w4 grad')
+    close(m.embed_fn.params.grad, Pg.grid.grad, 2e-3, 'grid grad')
+    close(m.uncert_grid.grad, Pg.uncert_grid.grad, 2e-3, 'uncert grad')
