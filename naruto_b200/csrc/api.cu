@@ -130,7 +130,7 @@ int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
     {
       const uint64_t span = 1ull + res + (uint64_t)res * res;
       d.lv[l].lim = size > span ? (uint32_t)(size - span) : 0u;
-      d.lv[l].pad_ = 0u;
+      d.lv[l].pad_[0] = d.lv[l].pad_[1] = d.lv[l].pad_[2] = 0u;
     }
     offset += size;
   }

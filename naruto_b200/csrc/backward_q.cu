@@ -25,7 +25,7 @@
 //             dh1 = W23^T da3 + W2[0]^T dsdf, da1 = mask1 * dh1              (3xTF32: data-gradient path)
 //             dfeat = W1[:, :32]^T da1                                       (3xTF32)  -> slot -> scatter warps -> red.global
 //             D += Y^T X                                                     (1-pass, own mbarrier, overlaps the next tile)
-// TMEM: [0,32) accumulator | [32,112) A_hi | [112,152) A_lo | [160,304) D.   Shared memory ~212 KB.
+// TMEM: [0,32) accumulator | [32,112) A_hi | [112,152) A_lo | [160,304) D | [320,352) dh3 | [352,368) dc hi / lo.   Shared memory ~213 KB.
 #include <cstdlib>
 
 #include "mlp_tc.cuh"
@@ -39,6 +39,9 @@
 #define Q_AHI 32
 #define Q_ALO 112
 #define Q_DW 160
+#define Q_ACC2 320                  // [320,352) dh3 (accumulators sit on 32-column boundaries)
+#define Q_DCH 352                   // [352,360) dc (hi), [360,368) dc (lo): A operand of dh3 = W4^T dc
+#define Q_DCL 360
 #define Q_BAR_MLP 1                 // named barrier of the 512 MLP threads
 
 // weights in shared memory (floats), chunk-major K-major B operands [K/4][rows][4]
@@ -48,8 +51,9 @@
 #define QW_B12L (QW_B12H + 40 * 32)
 #define QW_W1TH (QW_B12L + 40 * 32)      // [8][32][4]   dfeat[f] = sum_j da1[j] w1[j][f]
 #define QW_W1TL (QW_W1TH + 32 * 32)
-#define QW_W4 (QW_W1TL + 32 * 32)        // w4 as stored [3][32] (+ pad)
-#define QW_FLOATS (QW_W4 + 128)
+#define QW_W4TH (QW_W1TL + 32 * 32)      // [2][32][4]   dh3[j] = sum_i dc[i] w4[i][j]  (k = i < 3, padded to 8)
+#define QW_W4TL (QW_W4TH + 8 * 32)
+#define QW_FLOATS (QW_W4TL + 8 * 32)
 
 // transposed operands of the weight-gradient GEMM: buf[32 chunks of 4 points][R rows][4 points], R = 1 (mod 8)
 #define QX_ROWS 145                      // hash 0..31 | oneblob 32..79 | h1 80..111 | h3 112..143
@@ -167,7 +171,7 @@ __device__ __forceinline__ void q_scatter(const DevLevel* __restrict__ s_lv, con
       if (item >= 4 * NRT_L) break;
       const int lg = item >> 2;
       const int row = 32 * (item & 3) + lane;
-      const DevLevel& L = s_lv[lg];
+      const DevLevel L = s_lv[lg];                          // three 16-byte shared-memory loads (uniform)
       const bool active = pt0 + row < n_pts;
       const float x0 = slot[QS_X + row], x1 = slot[QS_X + 128 + row], x2 = slot[QS_X + 256 + row];
       const float2 g = *reinterpret_cast<const float2*>(slot + ((lg >> 1) * 128 + row) * 4 + (lg & 1) * 2);
@@ -193,17 +197,18 @@ __device__ __forceinline__ void q_scatter(const DevLevel* __restrict__ s_lv, con
         // every lane takes part in the shuffles; lanes without a gradient contribute zeros.
         // same[s]: the lane 2^s places further in this window of 2^agg lanes sits in the same cell
         const int wmask = (1 << L.agg) - 1;
+        // one key per cell: the low 10 bits of each coordinate.  Lanes of one window hold consecutive samples of a ray, whose
+        // cells are at most a few steps apart, so equal low bits <=> equal cell (coordinates differ by far less than 1024).
+        const uint32_t key = (p.g[0] & 1023u) | ((p.g[1] & 1023u) << 10) | ((p.g[2] & 1023u) << 20);
         bool same[3];
 #pragma unroll
         for (int sdx = 0; sdx < 3; ++sdx) {
           const int d = 1 << sdx;
-          const uint32_t o0 = __shfl_down_sync(0xffffffffu, p.g[0], d), o1 = __shfl_down_sync(0xffffffffu, p.g[1], d),
-                         o2 = __shfl_down_sync(0xffffffffu, p.g[2], d);
-          same[sdx] = ((lane & wmask) + d <= wmask) && o0 == p.g[0] && o1 == p.g[1] && o2 == p.g[2];
+          const uint32_t other = __shfl_down_sync(0xffffffffu, key, d);      // every lane shuffles (no short-circuit around it)
+          same[sdx] = ((lane & wmask) + d <= wmask) && other == key;
         }
-        const uint32_t q0 = __shfl_up_sync(0xffffffffu, p.g[0], 1), q1 = __shfl_up_sync(0xffffffffu, p.g[1], 1),
-                       q2 = __shfl_up_sync(0xffffffffu, p.g[2], 1);
-        const bool head = (lane & wmask) == 0 || !(q0 == p.g[0] && q1 == p.g[1] && q2 == p.g[2]);
+        const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane & wmask) == 0 || prev != key;
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
           float v[4] = {nz ? w[c] * g.x : 0.f, nz ? w[c] * g.y : 0.f, nz ? w[c + 1] * g.x : 0.f, nz ? w[c + 1] * g.y : 0.f};
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
     }
     raw3[t] = c0;
     if (t < 2016 - 1024) raw3[1024 + t] = c1;
-    if (t < 128) sw[QW_W4 + t] = d0;
+    if (t < 96) raw3[2016 + 32 + 1024 + t] = d0;          // w4 [3][32] behind W23
   }
   __syncthreads();
   if (trace && t == 0) g_q_trace[blockIdx.x * 8 + 6] = clock64();
@@ -337,6 +342,11 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
     const int o = ((j >> 2) * 32 + f) * 4 + (j & 3);
     q_put_split(sw, QW_W1TH + o, QW_W1TL + o, raw1[j * 80 + f]);
   }
+  for (int i = t; i < 8 * 32; i += Q_THREADS) {            // W4T[j][k] = w4[k][j] (k < 3)
+    const int j = i >> 3, k = i & 7;
+    const int o = ((k >> 2) * 32 + j) * 4 + (k & 3);
+    q_put_split(sw, QW_W4TH + o, QW_W4TL + o, k < 3 ? w23s[1024 + k * 32 + j] : 0.f);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -360,7 +370,6 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
     const uint32_t w_s = smem_u32(sw), xt_s = smem_u32(xt), yt_s = smem_u32(yt);
     float* xcol = xt + (row >> 2) * (QX_ROWS * 4) + (row & 3);
     float* ycol = yt + (row >> 2) * (QY_ROWS * 4) + (row & 3);
-    const float* w4s = sw + QW_W4;
     uint32_t ph_mma = 0u, ph_wg = 0u, par = 0u;
     int s = 0;
     const bool wtrace = (dbg & 8) && blockIdx.x < 8;
@@ -452,8 +461,17 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
         tmem_st16(lane_tb + Q_AHI + 32 + 16 * q, hi);
       } else {
         ycol[QY_DSDF * 4] = tf32_hi(dsdf);
+        float dch[8], dcl[8];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) ycol[(QY_DC + i) * 4] = tf32_hi(dc[i]);
+        for (int i = 0; i < 8; ++i) dch[i] = dcl[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          dch[i] = tf32_hi(dc[i]);
+          dcl[i] = dc[i] - dch[i];
+          ycol[(QY_DC + i) * 4] = dch[i];
+        }
+        tmem_st8(lane_tb + Q_DCH, dch);              // A operand of dh3 = W4^T dc (issued with phase 2)
+        tmem_st8(lane_tb + Q_DCL, dcl);
         // uncertainty grid: raw[..., 4] is the trilinear sample itself
         if (active && grads.uncert && du != 0.f) {
           const UncertPos up = uncert_pos(P, y0, y1, y2);
@@ -504,6 +522,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
         tc_fence_after();
         if (elect_one()) {
           q_issue_1p<80, 32>(tb + Q_ACC, tb + Q_AHI, w_s + QW_A3 * 4);
+          q_issue_3p<8, 32>(tb + Q_ACC2, tb + Q_DCH, tb + Q_DCL, w_s + QW_W4TH * 4, w_s + QW_W4TL * 4);   // dh3 = W4^T dc
           mma_commit(&bars->mma);
           // TMA: the next tile's inputs.  Its slot was last used by tile k - 2, which the scatter warps finished long ago
           if (k + 1 < my_tiles) {
@@ -523,16 +542,16 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
         QT1(tw_mma);
       }
       {
-        float a3[8], hi[8], lo[8];
+        float a3[8], dh3[8], hi[8], lo[8];
         tmem_ld8(lane_tb + Q_ACC + 8 * q, a3);
+        tmem_ld8(lane_tb + Q_ACC2 + 8 * q, dh3);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int j = 8 * q + i;
           xcol[(QX_H3 + j) * 4] = tf32_hi(fmaxf(a3[i], 0.f));
-          // dh3 = W4^T dc; da3 = dh3 * relu'
-          const float d = dc[0] * w4s[j] + dc[1] * w4s[32 + j] + dc[2] * w4s[64 + j];
-          const float v = (m3 >> i) & 1u ? d : 0.f;
+          // da3 = dh3 * relu'   (dh3 = W4^T dc came off the tensor core with a3)
+          const float v = (m3 >> i) & 1u ? dh3[i] : 0.f;
           hi[i] = tf32_hi(v);
           lo[i] = v - hi[i];
           ycol[(QY_DA3 + j) * 4] = hi[i];

@@ -20,7 +20,7 @@
 #define NRT_IN3 63        // 48 oneblob + 15 geo
 #define NRT_SMAX 256      // max samples per ray the ray kernels are built for
 
-struct DevLevel {
+struct __align__(16) DevLevel {       // 48 bytes: a warp reads its level's constants from shared memory with three 16-byte loads
   float scale;        // tcnn grid_scale(level)
   uint32_t res;       // tcnn grid_resolution(scale)
   uint32_t size;      // entries in this level (hashmap_size)
@@ -31,7 +31,7 @@ struct DevLevel {
   uint32_t agg;       // > 0: cells are coarse relative to the sample spacing: merge runs of up to 2^agg samples before the gradient RED
   uint32_t lim;       // dense levels: size - (1 + res + res2) (0 if that is negative): a cell whose base index is below lim has all
                       // eight corners inside [0, size) without uint32 wrap-around, so the % size is the identity
-  uint32_t pad_;
+  uint32_t pad_[3];
 };
 
 struct DevPlan {

@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
     __syncwarp();
     tmem_alloc<WS_COLS>(slot);
   }
-  load_weights_tc(sw, prm);
+  // (the ring area behind the weight block is free until the first tile: staging scratch; a __syncthreads() inside orders the
+  // barrier / TMEM set-up above as well)
+  load_weights_tc_staged<WS_THREADS>(sw, prm, sw + 2 * FW_FLOATS);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();

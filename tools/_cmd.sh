@@ -1,4 +1,10 @@
-timeout 1200 python -m pytest tests -x -q -m gpu -s > gpurun_out/r2n_tests.log 2>&1; tail -4 gpurun_out/r2n_tests.log; grep -E "rays within|bench shape" gpurun_out/r2n_tests.log | head -40
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 9 python -m pytest tests/test_scale_properties.py -x -q -m gpu -k "compositor or test_empty" > gpurun_out/r2n_racecheck_fwd.log 2>&1; echo "racecheck fwd rc=$?"; tail -5 gpurun_out/r2n_racecheck_fwd.log
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 9 python tools/probe_bwd.py 7 32 > gpurun_out/r2n_racecheck_bwd.log 2>&1; echo "racecheck bwd rc=$?"; tail -8 gpurun_out/r2n_racecheck_bwd.log
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_coslam_mapper.py tests/test_smoothness_golden.py "tests/test_scale_properties.py::test_backward_q_kernel_matches_round1_kernel" -x -q -m gpu -k "not 4096" > gpurun_out/r2n_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -5 gpurun_out/r2n_memcheck.log
+timeout 400 python -m pytest tests/test_scale_properties.py tests/test_cuda_parity.py tests/test_mapper.py -x -q -m gpu > gpurun_out/r2r_tests.log 2>&1; tail -3 gpurun_out/r2r_tests.log
+P="python tools/probe_bwd.py"
+PROBE_WARPS=1 NRT_BWD_DEBUG=8 timeout 100 $P 4096 117 > gpurun_out/r2r_probe.log 2>&1
+NRT_BWD_DEBUG=8 timeout 100 $P 32768 117 >> gpurun_out/r2r_probe.log 2>&1
+NRT_BWD_DEBUG=8 timeout 100 $P 2148 32 >> gpurun_out/r2r_probe.log 2>&1
+NRT_BWD_IMPL=tc timeout 100 $P 4096 117 >> gpurun_out/r2r_probe.log 2>&1
+grep -v "mlp \|scat " gpurun_out/r2r_probe.log | tail -32; grep " 0 scat\| 8 scat\|16 mlp\|17 mlp" gpurun_out/r2r_probe.log | head -4
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-torch-gpu-baseline --no-side-configs --no-dropin > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err
+python -c "
+import json;d=json.load(open('gpurun_out/r2r_bench.json'));print(d['value'],d['ms_per_step'],d['kernels'],d['roofline']['frac'],d['sweep']['ms'],d['sweep']['frac_of_hbm_peak'])"
