@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
                                                                     const float* __restrict__ feat,
                                                                     const uint32_t* __restrict__ masks,
                                                                     const float* __restrict__ draw, const NrtGrads grads, float* __restrict__ wg_part,
-                                                                    int dbg) {
+                                                                    unsigned int* __restrict__ wg_counter, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   QBars* bars = reinterpret_cast<QBars*>(smem_raw);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(smem_raw + 192);
@@ -657,6 +657,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
     if (any_tile) q_wait(&bars->wg, ph_wg);           // the last tile's weight-gradient GEMM
   }
 
+  if (blockIdx.x == 0 && t == 0) *wg_counter = 0u;        // arms the reduction kernel's last-block counter (scratch is uninitialised)
   // ---- hand this CTA's weight-gradient block to the reduction kernel: rows 0..67 of D -> wg_part[blockIdx.x][68][144] ----
   tc_fence_before();
   __syncthreads();
@@ -703,14 +704,25 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
 // Block 0 owns M and the two contractions; blocks 1..33 the 4224 elements that go straight into a gradient tensor.
 // ---------------------------------------------------------------------------------------------
 // Thread layout: consecutive lanes take consecutive elements (coalesced reads of every partial block); the eight 128-thread
-// groups of a block take the partials c = g, g + 8, ... in order and meet through shared memory in group order.
+// groups of a block take the partials c = g, g + 8, ... (all loads of a thread in flight together) and meet through shared
+// memory in group order.  Blocks 0..32: the 4224 elements that go straight into a gradient tensor.  Blocks 33..40: M, 128
+// elements each, into a global scratch; the last of them to finish (counter) runs the two contractions, which need all of M.
 __device__ __forceinline__ float wg_sum(const float* __restrict__ part, int n_part, int e, int grp) {
+  // up to 24 partial blocks per group (n_part <= 192 CTAs): every load is issued before the first add -- one trip to L2
+  float v[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const int c = grp + 8 * i;
+    v[i] = c < n_part ? __ldg(part + (int64_t)c * (QY_LIVE * 144) + e) : 0.f;
+  }
   float acc = 0.f;
-  for (int c = grp; c < n_part; c += 8) acc += __ldg(part + (int64_t)c * (QY_LIVE * 144) + e);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) acc += v[i];            // fixed order
+  for (int c = grp + 192; c < n_part; c += 8) acc += __ldg(part + (int64_t)c * (QY_LIVE * 144) + e);
   return acc;
 }
 
-__device__ __forceinline__ int wg_route(int e, int& src, const NrtGrads& grads, float*& dst) {
+__device__ __forceinline__ void wg_route(int e, int& src, const NrtGrads& grads, float*& dst) {
   // direct elements: 2560 (dW1) + 1536 (dW3 oneblob part) + 32 (dW2 row 0) + 96 (dW4) = 4224
   if (e < 2560) {
     src = (e / 80) * 144 + e % 80;
@@ -727,59 +739,65 @@ __device__ __forceinline__ int wg_route(int e, int& src, const NrtGrads& grads, 
     src = (QY_DC + u / 32) * 144 + QX_H3 + u % 32;
     dst = grads.w4 ? grads.w4 + u : nullptr;
   }
-  return 0;
 }
 
+#define WG_DIRECT_BLOCKS (4224 / 128)
+#define WG_M_BLOCKS 8
+
 __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restrict__ part, int n_part, const NrtParams prm,
-                                                            const NrtGrads grads) {
+                                                            const NrtGrads grads, float* __restrict__ m_glob,
+                                                            unsigned int* __restrict__ counter) {
   __shared__ float s_sum[8][128];
   __shared__ float Ms[32 * 33];
+  __shared__ unsigned int s_last;
   const int t = threadIdx.x, grp = t >> 7, el = t & 127;
-  if (blockIdx.x == 0) {
-    // M = da3^T h1: 1024 elements in eight passes of 128, then the contractions (they need all of M)
-    for (int e0 = 0; e0 < 1024; e0 += 128) {
-      const int e = e0 + el;
-      s_sum[grp][el] = wg_sum(part, n_part, (32 + (e >> 5)) * 144 + QX_H1 + (e & 31), grp);
-      __syncthreads();
-      if (grp == 0) {
-        float v = 0.f;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) v += s_sum[g][el];
-        Ms[(e >> 5) * 33 + (e & 31)] = v;
-      }
-      __syncthreads();
-    }
-    if (t < 480) {
-      if (grads.w3) {
-        const int j = t / NRT_GEO, g = t % NRT_GEO;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int m = 0; m < 32; ++m) acc = fmaf(Ms[j * 33 + m], __ldg(prm.w2 + (1 + g) * 32 + m), acc);
-        grads.w3[j * 63 + NRT_OB + g] += acc;
-      }
-    } else if (t >= 512 && t < 992) {
-      if (grads.w2) {
-        const int u = t - 512;
-        const int g = u >> 5, m = u & 31;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < 32; ++j) acc = fmaf(__ldg(prm.w3 + j * 63 + NRT_OB + g), Ms[j * 33 + m], acc);
-        grads.w2[(1 + g) * 32 + m] += acc;
-      }
-    }
-    return;
+  const bool m_block = blockIdx.x >= WG_DIRECT_BLOCKS;
+  int e, src;
+  float* dst = nullptr;
+  if (m_block) {
+    e = (blockIdx.x - WG_DIRECT_BLOCKS) * 128 + el;         // M = da3^T h1, element (j, m) = (e >> 5, e & 31)
+    src = (32 + (e >> 5)) * 144 + QX_H1 + (e & 31);
+  } else {
+    e = blockIdx.x * 128 + el;
+    wg_route(e, src, grads, dst);
   }
-  const int e = (blockIdx.x - 1) * 128 + el;             // 4224 = 33 x 128 direct elements
-  int src;
-  float* dst;
-  wg_route(e, src, grads, dst);
   s_sum[grp][el] = wg_sum(part, n_part, src, grp);
   __syncthreads();
-  if (grp == 0 && dst) {
+  if (grp == 0) {
     float v = 0.f;
 #pragma unroll
     for (int g = 0; g < 8; ++g) v += s_sum[g][el];
-    *dst += v;
+    if (m_block) m_glob[e] = v;
+    else if (dst) *dst += v;
+  }
+  if (!m_block) return;
+  // ---- the last M block contracts: dW3[j][48+g] = sum_m M[j][m] W2[1+g][m];  dW2[1+g][m] = sum_j W3[j][48+g] M[j][m] ----
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_last = atomicAdd(counter, 1u) == WG_M_BLOCKS - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  Ms[(t >> 5) * 33 + (t & 31)] = __ldcg(m_glob + t);
+  if (t == 0) *counter = 0u;                                // re-arm for the next launch
+  __syncthreads();
+  if (t < 480) {
+    if (grads.w3) {
+      const int j = t / NRT_GEO, g = t % NRT_GEO;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int m = 0; m < 32; ++m) acc = fmaf(Ms[j * 33 + m], __ldg(prm.w2 + (1 + g) * 32 + m), acc);
+      grads.w3[j * 63 + NRT_OB + g] += acc;
+    }
+  } else if (t >= 512 && t < 992) {
+    if (grads.w2) {
+      const int u = t - 512;
+      const int g = u >> 5, m = u & 31;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) acc = fmaf(__ldg(prm.w3 + j * 63 + NRT_OB + g), Ms[j * 33 + m], acc);
+      grads.w2[(1 + g) * 32 + m] += acc;
+    }
   }
 }
 
@@ -793,7 +811,8 @@ int q_trace_read(void* dst, int bytes) {
   return NRT_OK;
 }
 
-int64_t decode_bwd_q_scratch_floats(const NrtPlan* plan) { return (int64_t)plan->sm_count * QY_LIVE * 144; }
+// per-CTA weight-gradient blocks | M (1024) | counter
+int64_t decode_bwd_q_scratch_floats(const NrtPlan* plan) { return (int64_t)plan->sm_count * QY_LIVE * 144 + 1024 + 32; }
 
 int launch_decode_bwd_q(const NrtPlan* plan, const NrtParams* prm, const float* rays_o, const float* rays_d, const float* z, int S,
                         int64_t n_pts, const float* feat, const uint32_t* masks, const float* draw, const NrtGrads* grads,
@@ -808,10 +827,13 @@ int launch_decode_bwd_q(const NrtPlan* plan, const NrtParams* prm, const float* 
     const char* e = getenv("NRT_BWD_DEBUG");
     return e ? atoi(e) : 0;
   }();
-  decode_bwd_q_kernel<<<blocks, Q_THREADS, Q_SMEM_BYTES, st>>>(plan->dev, *prm, rays_o, rays_d, z, S, n_pts, feat, masks, draw, *grads, wg_part, dbg);
+  decode_bwd_q_kernel<<<blocks, Q_THREADS, Q_SMEM_BYTES, st>>>(plan->dev, *prm, rays_o, rays_d, z, S, n_pts, feat, masks, draw, *grads, wg_part,
+                                                               reinterpret_cast<unsigned int*>(wg_part + (int64_t)plan->sm_count * QY_LIVE * 144 + 1024), dbg);
   NRT_CUDA_CHECK(cudaGetLastError());
   if (grads->w1 || grads->w2 || grads->w3 || grads->w4) {
-    wgrad_reduce_kernel<<<1 + 4224 / 128, 1024, 0, st>>>(wg_part, blocks, *prm, *grads);
+    float* m_glob = wg_part + (int64_t)plan->sm_count * QY_LIVE * 144;
+    wgrad_reduce_kernel<<<WG_DIRECT_BLOCKS + WG_M_BLOCKS, 1024, 0, st>>>(wg_part, blocks, *prm, *grads, m_glob,
+                                                                          reinterpret_cast<unsigned int*>(m_glob + 1024));
     NRT_CUDA_CHECK(cudaGetLastError());
   }
   return NRT_OK;

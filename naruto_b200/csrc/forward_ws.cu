@@ -364,15 +364,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
     __syncthreads();
     if (threadIdx.x == 0) *s_last = atomicAdd(lf.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
     __syncthreads();
-    if (*s_last && threadIdx.x < NRT_N_STATS) {
+    if (*s_last) {
+      // The last CTA folds the per-CTA partials: 16 groups of 16 threads take every 16th CTA each (all their loads in flight at
+      // once), then one thread per statistic adds the 16 group sums in group order -- a fixed tree, so the result does not
+      // depend on scheduling.  (A single thread per statistic walking all CTAs in a dependent chain cost ~13 us of exposed L2
+      // latency at the end of every training forward.)
       __threadfence();
-      double v = threadIdx.x == NRT_STAT_UNCERT_MIN ? 3.4e38 : 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) {
-        const double pv = lf.part[(int64_t)b * NRT_N_STATS + threadIdx.x];
-        v = threadIdx.x == NRT_STAT_UNCERT_MIN ? fmin(v, pv) : v + pv;
+      double* grp = all;                          // [16 groups][16 stats], the ring area is idle
+      if (threadIdx.x < 256) {
+        const int k = threadIdx.x & 15, j = threadIdx.x >> 4;
+        double v = k == NRT_STAT_UNCERT_MIN ? 3.4e38 : 0.0;
+        for (unsigned b = j; b < gridDim.x; b += 16) {
+          const double pv = lf.part[(int64_t)b * NRT_N_STATS + k];
+          v = k == NRT_STAT_UNCERT_MIN ? fmin(v, pv) : v + pv;
+        }
+        grp[j * 16 + k] = v;
       }
-      lf.stats[threadIdx.x] = v;
-      if (threadIdx.x == 0) *lf.counter = 0u;   // re-arm for the next launch
+      __syncthreads();
+      if (threadIdx.x < NRT_N_STATS) {
+        const int k = threadIdx.x;
+        double v = k == NRT_STAT_UNCERT_MIN ? 3.4e38 : 0.0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v = k == NRT_STAT_UNCERT_MIN ? fmin(v, grp[j * 16 + k]) : v + grp[j * 16 + k];
+        lf.stats[k] = v;
+        if (k == 0) *lf.counter = 0u;   // re-arm for the next launch
+      }
     }
     if (lf.losses) {                            // one shard = the whole batch: the losses follow at once (no extra launch)
       __syncthreads();

@@ -12,7 +12,11 @@ from oracle import tcnn_shim
 
 
 def test_anchor_level_table(spec):
-    # resolutions, entries per level, total parameter count at office0
+    # resolutions, entries per level, total parameter count at office0.
+    # Caveat at the unpinned tcnn boundary: the shim (and csrc/api.cu) evaluate grid_scale in fp64 and round once, real tcnn in
+    # fp32 (exp2f(level * log2f(s)) * base - 1).  The top level's scale is exactly 274.0 in real arithmetic, so tcnn's
+    # ceil() + 1 can land on 275 or 276 there; the level is hashed, so its resolution only enters through the hash of the
+    # cell coordinates (scale-driven), not through a stride -- the features are unaffected either way.
     assert [lv['res'] for lv in spec.table] == [16, 20, 24, 29, 35, 42, 50, 61, 73, 89, 107, 129, 156, 189, 228, 275]
     assert [lv['size'] for lv in spec.table] == [4096, 8000, 13824, 24392, 42880] + [65536] * 11
     assert spec.n_grid_entries * spec.n_features == 1628176
