@@ -304,8 +304,11 @@ int nrt_pack_frame(const float* direction, const float* rgb, const float* depth,
 /* count (dev int32, overwritten) of pixels with 0 < depth <= depth_trunc (src/slam/coslam/coslam.py:319-321) */
 int nrt_valid_depth_count(const float* frame_rays, int64_t n_pixels, float depth_trunc, int32_t* count, void* stream);
 /* KeyFrameDatabaseNaruto.add_keyframe (src/slam/coslam/model/keyframe.py:21-60): slot[i] = frame_rays[idxs[i % n_idx]]
- * for i < rays_per_kf (the reference doubles the selected rows until there are enough of them) */
-int nrt_kf_store(const float* frame_rays, const int64_t* idxs, int64_t n_idx, int32_t rays_per_kf, float* slot, void* stream);
+ * for i < rays_per_kf (the reference doubles the selected rows until there are enough of them).  n_valid_dev (optional, dev
+ * int32): the valid-depth pixel count the indices were drawn from; when it is 0 the slot is left untouched, like the reference,
+ * which attaches the frame id and returns before storing (rays.shape[1] == 0). */
+int nrt_kf_store(const float* frame_rays, const int64_t* idxs, int64_t n_idx, int32_t rays_per_kf, const int32_t* n_valid_dev,
+                 float* slot, void* stream);
 /* random.sample(range(n), k): k distinct uniform indices (a keyed bijection of [0,n), seed-deterministic).  If n_dev != NULL
  * the population size is read from that device int32 (e.g. the valid-depth count), otherwise `n` is used. */
 int nrt_sample_indices(int64_t n, const int32_t* n_dev, int64_t k, uint64_t seed, int64_t* out, void* stream);

@@ -103,7 +103,7 @@ SIGNATURES = {
     'nrt_camera_rays': (C.c_int, [C.c_int32, C.c_int32, c_f, c_f, c_f, c_f, c_fp, _P]),
     'nrt_pack_frame': (C.c_int, [c_fp, c_fp, c_fp, C.c_int64, c_fp, _P]),
     'nrt_valid_depth_count': (C.c_int, [c_fp, C.c_int64, c_f, c_fp, _P]),
-    'nrt_kf_store': (C.c_int, [c_fp, c_fp, C.c_int64, C.c_int32, c_fp, _P]),
+    'nrt_kf_store': (C.c_int, [c_fp, c_fp, C.c_int64, C.c_int32, c_fp, c_fp, _P]),
     'nrt_sample_indices': (C.c_int, [C.c_int64, c_fp, C.c_int64, C.c_uint64, c_fp, _P]),
     'nrt_assemble_rays': (C.c_int, [c_fp, c_fp, C.c_int32, C.c_int32, c_fp, C.c_int64, c_fp, c_fp, C.c_int64, c_fp, C.c_int32,
                                     c_fp, c_fp, c_fp, c_fp, _P]),

@@ -51,7 +51,7 @@ int launch_adam_peers(const NrtPeerTable*, float*, float*, const NrtAdamGroup*, 
 int launch_camera_rays(int, int, float, float, float, float, float*, cudaStream_t);
 int launch_pack_frame(const float*, const float*, const float*, int64_t, float*, cudaStream_t);
 int launch_valid_depth_count(const float*, int64_t, float, int*, cudaStream_t);
-int launch_kf_store(const float*, const int64_t*, int64_t, int, float*, cudaStream_t);
+int launch_kf_store(const float*, const int64_t*, int64_t, int, const int*, float*, cudaStream_t);
 int launch_feistel_sample(int64_t, int64_t, uint64_t, const int*, int64_t*, cudaStream_t);
 int launch_assemble_rays(const float*, const int64_t*, int, int, const int64_t*, int64_t, const float*, const int64_t*, int64_t,
                          const float*, int, float*, float*, float*, float*, cudaStream_t);
@@ -126,6 +126,8 @@ int nrt_plan_create(const NrtConfig* cfg, NrtPlan** out) {
     d.lv[l].hashed = ((uint64_t)res * res * res > size) ? 1u : 0u;
     d.lv[l].res2 = res * res;
     d.lv[l].magic = (uint32_t)((1ull << 32) / size);
+    // run merging in the backward scatter: window of 2^agg consecutive samples (cells coarse relative to the sample spacing)
+    // (a window of 2 on the next levels, res <= 110, was measured neutral and is not used)
     d.lv[l].agg = res <= 32u ? 3u : res <= 64u ? 2u : 0u;
     {
       const uint64_t span = 1ull + res + (uint64_t)res * res;
@@ -446,9 +448,10 @@ int nrt_valid_depth_count(const float* frame_rays, int64_t n_pixels, float depth
   return launch_valid_depth_count(frame_rays, n_pixels, depth_trunc, count, (cudaStream_t)stream);
 }
 
-int nrt_kf_store(const float* frame_rays, const int64_t* idxs, int64_t n_idx, int32_t rays_per_kf, float* slot, void* stream) {
+int nrt_kf_store(const float* frame_rays, const int64_t* idxs, int64_t n_idx, int32_t rays_per_kf, const int32_t* n_valid_dev, float* slot,
+                 void* stream) {
   NRT_REQUIRE(frame_rays && idxs && slot && n_idx > 0 && rays_per_kf > 0, "kf_store arguments");
-  return launch_kf_store(frame_rays, idxs, n_idx, rays_per_kf, slot, (cudaStream_t)stream);
+  return launch_kf_store(frame_rays, idxs, n_idx, rays_per_kf, n_valid_dev, slot, (cudaStream_t)stream);
 }
 
 int nrt_sample_indices(int64_t n, const int32_t* n_dev, int64_t k, uint64_t seed, int64_t* out, void* stream) {

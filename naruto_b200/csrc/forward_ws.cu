@@ -18,6 +18,9 @@
 // warps integrate along the rays (warp per ray).  Named barriers carry the ring (full / empty per stage), the MLP group's
 // publish step and the sub-CTA phases; the two sub-CTAs share only the weights in shared memory and the TMEM allocation.
 // The gather warps never wait for a tensor-core phase, so the L1 pipe stays busy; the weights are staged once per SM.
+// Measured and dropped for tables beyond L2 (T = 2^21, round 2): `prefetch.global.L2` of the next batch of levels by the gather
+// warps (forward 0.83 -> 0.92 ms: the prefetches cost LSU slots the loads need; at T = 2^16 0.173 -> 0.238 ms) and interleaving
+// dense and hashed levels between the two halves of a gather set (0.81 -> 0.83 ms).
 #include "common.cuh"
 #include "mlp_tc.cuh"
 

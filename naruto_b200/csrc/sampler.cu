@@ -52,10 +52,14 @@ __global__ void __launch_bounds__(256) valid_depth_count_kernel(const float* __r
 }
 
 // dst[i] = frame[idxs[i % n_idx]]: the reference doubles the selected rows until there are at least P of them
+// n_valid_dev (optional): device count of valid-depth pixels the indices were drawn from; when it is 0 the slot is left untouched,
+// as the reference does (it attaches the frame id and returns before storing when no pixel has a valid depth)
 __global__ void __launch_bounds__(256) kf_store_kernel(const float* __restrict__ frame, const int64_t* __restrict__ idxs,
-                                                       int64_t n_idx, int P, float* __restrict__ dst) {
+                                                       int64_t n_idx, int P, const int* __restrict__ n_valid_dev,
+                                                       float* __restrict__ dst) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)P * 7) return;
+  if (n_valid_dev && *n_valid_dev <= 0) return;
   const int64_t i = t / 7;
   const int k = (int)(t - i * 7);
   dst[t] = frame[idxs[i % n_idx] * 7 + k];
@@ -304,8 +308,8 @@ int launch_valid_depth_count(const float* rays, int64_t n, float depth_trunc, in
   return NRT_OK;
 }
 
-int launch_kf_store(const float* frame, const int64_t* idxs, int64_t n_idx, int P, float* dst, cudaStream_t st) {
-  kf_store_kernel<<<blocks_for((int64_t)P * 7), 256, 0, st>>>(frame, idxs, n_idx, P, dst);
+int launch_kf_store(const float* frame, const int64_t* idxs, int64_t n_idx, int P, const int* n_valid_dev, float* dst, cudaStream_t st) {
+  kf_store_kernel<<<blocks_for((int64_t)P * 7), 256, 0, st>>>(frame, idxs, n_idx, P, n_valid_dev, dst);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

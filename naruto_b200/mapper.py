@@ -34,6 +34,7 @@ class FusedState:
         # Data parallel: parameters and the gradient bucket live in NVLink-mapped symmetric memory when it is available, and the
         # two exchanges of the iteration run inside our own kernels (csrc/peer.cu); NRT_DP_IMPL=nccl forces the NCCL all-reduces
         self.peers = None
+        self.pg = process_group
         if process_group is not None and torch.distributed.get_world_size(process_group) > 1 \
                 and os.environ.get('NRT_DP_IMPL', 'peer') != 'nccl' and self.dev.type == 'cuda':
             try:
@@ -95,8 +96,36 @@ class FusedState:
         self.sync_optimizers()
         return self
 
-    def sync_optimizers(self):
-        """Write the fused Adam state into the bound torch optimisers (views for the moments, host step counts)."""
+    def owned_ranges(self, rank=None, world=None):
+        """Float ranges [lo, hi) of the flat vector whose Adam moments THIS rank maintains under the peer-memory exchange
+        (csrc/peer.cu: rank r owns float4s [b4 + n4*r/W, b4 + n4*(r+1)/W) of every parameter group)."""
+        if self.peers is None:
+            return [(0, self.total)]
+        W = self.peers.world if world is None else world
+        R = self.peers.rank if rank is None else rank
+        out, ng, nd = [], self.n_grid, self.n_dec
+        for b, e in ((0, ng), (ng, ng + nd), (ng + nd, self.total)):
+            b4, n4 = b // 4, (e + 3) // 4 - b // 4
+            out.append((4 * (b4 + n4 * R // W), min(4 * (b4 + n4 * (R + 1) // W), self.total)))
+        return out
+
+    def gather_moments(self):
+        """Peer-memory data parallelism shards the Adam moments (every rank steps 1/N of each group): make exp_avg / exp_avg_sq
+        complete on every rank again, e.g. before `save_ckpt` reads `optimizer.state_dict()`.  One all-reduce of two masked copies."""
+        if self.peers is None:
+            return
+        for m in (self.exp_avg, self.exp_avg_sq):
+            full = torch.zeros_like(m)
+            for lo, hi in self.owned_ranges():
+                full[lo:hi] = m[lo:hi]
+            torch.distributed.all_reduce(full, group=self.pg)
+            m.copy_(full)
+
+    def sync_optimizers(self, gather=True):
+        """Write the fused Adam state into the bound torch optimisers (views for the moments, host step counts); at N > 1 with
+        sharded moments, all-gather them first (gather=False skips that)."""
+        if gather:
+            self.gather_moments()
         if self._bound is None:
             return
         model, map_opt, unc_opt = self._bound

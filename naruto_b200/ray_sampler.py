@@ -102,11 +102,13 @@ class DeviceKeyFrameDatabase:
         dev = self.device
         frame = pack_frame(batch['direction'].to(dev), batch['rgb'].to(dev), batch['depth'].to(dev))
         P = self.num_rays_to_save
+        cnt = None
         if idxs is None:
             if filter_depth:
                 cnt = valid_depth_count(frame, self.config['cam']['depth_trunc'])
                 # the reference draws min(num_valid, P) indices; drawing P from a smaller population repeats indices, which is
-                # what its doubling rule produces as well
+                # what its doubling rule produces as well.  A frame with NO valid pixel leaves the slot untouched (the count
+                # goes to the store kernel), like the reference, which attaches the id and returns before storing.
                 idxs = sample_indices(0, P, self._next_seed(), dev, n_dev=cnt)
                 n_valid = None
             else:
@@ -120,7 +122,8 @@ class DeviceKeyFrameDatabase:
         if n_valid == 0:
             return
         slot = self.rays[self._n - 1]
-        L.check(self.lib.nrt_kf_store(L.ptr(frame), L.ptr(idxs), idxs.shape[0], P, L.ptr(slot), _stream()))
+        L.check(self.lib.nrt_kf_store(L.ptr(frame), L.ptr(idxs), idxs.shape[0], P, L.ptr(cnt) if cnt is not None else None,
+                                      L.ptr(slot), _stream()))
 
     def sample_global_rays(self, bs, idxs=None):
         """third_parties/coslam/model/keyframe.py:69-79 -> (rays [bs,7], frame_ids [bs]) device tensors."""

@@ -78,3 +78,21 @@ def test_shard_range_edges():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_owned_ranges_tile_every_group():
+    """The host-side ownership map of the sharded Adam moments (FusedState.owned_ranges) mirrors csrc/peer.cu: for every world
+    size the ranks' ranges tile each parameter group exactly, in float4 units."""
+    import types
+    from naruto_b200.mapper import FusedState
+    for n_grid, n_dec, n_unc in ((1628176, 5184, 96040), (38452256, 5184, 929016), (1628176, 5184, 993531)):
+        st = types.SimpleNamespace(n_grid=n_grid, n_dec=n_dec, total=n_grid + n_dec + n_unc, peers=types.SimpleNamespace(world=1, rank=0))
+        for world in (2, 3, 4, 8):
+            cover = [0] * 3
+            prev_hi = [0, n_grid, n_grid + n_dec]
+            for rank in range(world):
+                rs = FusedState.owned_ranges(st, rank=rank, world=world)
+                for g, (lo, hi) in enumerate(rs):
+                    assert lo == prev_hi[g] and lo % 4 == 0 and hi >= lo
+                    prev_hi[g] = hi
+            assert prev_hi == [n_grid, n_grid + n_dec, st.total]

@@ -63,9 +63,12 @@ def _worker(rank, world, port, impl, out_dir):
             torch.cuda.synchronize()
             log['ref_losses'].append(ref.losses[:5].cpu())
             log['ref_totals'].append(ref.total_loss())
+    ms.state.gather_moments()                 # peer memory shards the Adam moments: make them whole again (save_ckpt)
     log['theta'] = ms.theta.cpu()
+    log['exp_avg'] = ms.exp_avg.cpu()
     if ref is not None:
         log['ref_theta'] = ref.theta.cpu()
+        log['ref_exp_avg'] = ref.exp_avg.cpu()
         log['sizes'] = ms.state.sizes
     torch.save(log, os.path.join(out_dir, f'{impl}_{rank}.pt'))
     dist.barrier()
@@ -100,3 +103,7 @@ def test_two_ranks_equal_one_rank_on_the_concatenated_batch(tmp_path, impl):
         assert ok >= frac, (name, ok)
         off += n
     assert (r0['theta'][-r0['sizes'][5]:] - 3.0).abs().max() > 0.1, 'the uncertainty grid took its Adam step'
+    # the (gathered) first moments are complete and the same on both ranks, and they are the single-GPU run's
+    assert torch.equal(r0['exp_avg'], r1['exp_avg'])
+    dm = (r0['exp_avg'] - r0['ref_exp_avg']).abs()
+    assert dm.max() <= 2e-3 * r0['ref_exp_avg'].abs().max(), (dm.max(), r0['ref_exp_avg'].abs().max())

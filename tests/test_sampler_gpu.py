@@ -122,3 +122,23 @@ def test_full_size_batch_on_device():
     assert o.shape == (2048 + -(-n_cur // 4), 3) and t.shape == (o.shape[0], 1)
     assert torch.isfinite(o).all() and torch.isfinite(d).all() and bool((t >= 0).all())
     assert bool((d[:, 2] == -1.0).all())                                     # identity rotations: z of the camera ray
+
+
+def test_keyframe_with_no_valid_depth_leaves_its_slot_untouched():
+    """filter_depth with device-drawn indices: a frame without a single valid-depth pixel attaches its id and stores nothing,
+    like the reference (src/slam/coslam/model/keyframe.py:47-52: rays.shape[1] == 0 -> return)."""
+    from naruto_b200.configs import replica_office0
+    from naruto_b200.ray_sampler import DeviceKeyFrameDatabase
+    cfg = replica_office0()
+    H, W, P = 24, 32, 40
+    db = DeviceKeyFrameDatabase(cfg, H, W, 4, P, 'cuda')
+    g = torch.Generator().manual_seed(0)
+    good = {'frame_id': torch.tensor([0]), 'direction': torch.rand(1, H, W, 3, generator=g), 'rgb': torch.rand(1, H, W, 3, generator=g),
+            'depth': torch.rand(1, H, W, generator=g) + 0.5}
+    bad = dict(good, frame_id=torch.tensor([5]), depth=torch.zeros(1, H, W))
+    db.add_keyframe(good, filter_depth=True)
+    db.add_keyframe(bad, filter_depth=True)
+    torch.cuda.synchronize()
+    assert len(db) == 2 and db.frame_ids.tolist() == [0, 5]
+    assert db.rays[0].abs().sum() > 0 and (db.rays[0, :, 6] > 0).all()
+    assert db.rays[1].abs().sum() == 0, 'no pixel of an all-invalid frame is stored'
