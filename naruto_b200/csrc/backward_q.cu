@@ -68,7 +68,8 @@
 #define QX_FLOATS (32 * QX_ROWS * 4)
 #define QY_FLOATS (32 * QY_ROWS * 4 + (128 - QY_ROWS) * 4)   // the MMA reads 128 rows per chunk: slack behind the last chunk
 
-// ring slot (floats): features in / feature gradients out, chunk-major [8 chunks][128 rows][4]
+// ring slot (floats): features in (chunk-major [8 chunks][128 rows][4], as saved by the forward) / feature gradients out
+// (level-major [16 levels][128 rows][2])
 #define QS_X 4096                        // x0[128] x1[128] x2[128]   (written by the MLP threads, read by the scatter warps)
 #define QS_DRAW 4480                     // dL/d raw [128][5]         (TMA)
 #define QS_MASK 5120                     // ReLU masks [128][2] words (TMA)
@@ -146,7 +147,7 @@ __device__ __forceinline__ void q_prefetch(float* slot, uint64_t* full, int64_t 
 // contributions of the following lanes of its window that sit in the same cell, and only the first lane of each run issues
 // the reductions (same procedure as backward_tc.cu).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void q_scatter(const DevLevel* __restrict__ s_lv, const float* __restrict__ slots, QBars* bars,
+__device__ __forceinline__ void q_scatter(const DevPlan& P, const float* __restrict__ slots, QBars* bars,
                                           int* __restrict__ s_cnt, float2* __restrict__ dgrid, int my_tiles, int64_t n_pts, int dbg) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int s = 0;
@@ -171,10 +172,12 @@ __device__ __forceinline__ void q_scatter(const DevLevel* __restrict__ s_lv, con
       if (item >= 4 * NRT_L) break;
       const int lg = item >> 2;
       const int row = 32 * (item & 3) + lane;
-      const DevLevel L = s_lv[lg];                          // three 16-byte shared-memory loads (uniform)
+      // level constants straight from the kernel-parameter constant bank (warp-uniform index: constant-cache reads, no LSU
+      // traffic -- the shared-memory copy cost 185 wavefronts per tile on the pipe that bounds this kernel)
+      const DevLevel& L = P.lv[lg];
       const bool active = pt0 + row < n_pts;
       const float x0 = slot[QS_X + row], x1 = slot[QS_X + 128 + row], x2 = slot[QS_X + 256 + row];
-      const float2 g = *reinterpret_cast<const float2*>(slot + ((lg >> 1) * 128 + row) * 4 + (lg & 1) * 2);
+      const float2 g = *reinterpret_cast<const float2*>(slot + (lg * 128 + row) * 2);      // level-major: 256 contiguous bytes per warp
       const bool nz = active && (g.x != 0.f || g.y != 0.f);
       if (!__any_sync(0xffffffffu, nz)) continue;          // e.g. 32 samples behind the surface: nothing to add
       uint32_t idx[8];
@@ -263,7 +266,6 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
   float* xt = sw + QW_FLOATS;
   float* yt = xt + QX_FLOATS;
   float* slots = yt + QY_FLOATS;
-  __shared__ DevLevel s_lv[NRT_L];
   __shared__ int s_cnt[Q_NSLOT];                       // next scatter work item of the tile in each ring slot
   const int t = threadIdx.x;
   const int64_t n_tiles = (n_pts + 127) / 128;
@@ -288,7 +290,6 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
     __syncwarp();
     tmem_alloc<Q_COLS>(tslot);
   }
-  if (t < NRT_L) s_lv[t] = P.lv[t];
   // raw weights -> shared memory (coalesced, one round trip), W23 = W3[:, 48:63] W2[1:16, :] formed ONCE per CTA from there
   // (the X^T region is free until the first tile): every operand image below is then built from shared memory
   float* raw1 = xt;                  // w1 [32][80]
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
   if (trace && t == 0) g_q_trace[blockIdx.x * 8 + 1] = clock64();
 
   if (t < Q_SCAT) {
-    q_scatter(s_lv, slots, bars, s_cnt, reinterpret_cast<float2*>(grads.grid), my_tiles, n_pts, dbg);
+    q_scatter(P, slots, bars, s_cnt, reinterpret_cast<float2*>(grads.grid), my_tiles, n_pts, dbg);
     if (trace && t == 0) g_q_trace[blockIdx.x * 8 + 3] = clock64();
   } else {
     // ------------------------------------------------------------------------------------------
@@ -629,9 +630,11 @@ __global__ void __launch_bounds__(Q_THREADS, 1) decode_bwd_q_kernel(const __grid
         float df[8];
         tmem_ld8(lane_tb + Q_ACC + 8 * q, df);
         tmem_ld_wait();
-        // the slot's feature area now takes the feature gradients (this thread overwrites exactly what it read above)
-        sts4(slot + ((2 * q) * 128 + row) * 4, df[0], df[1], df[2], df[3]);
-        sts4(slot + ((2 * q + 1) * 128 + row) * 4, df[4], df[5], df[6], df[7]);
+        // the slot's feature area now takes the feature gradients, level-major [16 levels][128 rows][2] (what a scatter warp
+        // reads per item is then 256 contiguous bytes).  The features were stored chunk-major, so other threads' reads of this
+        // area must be over before anybody overwrites it: they are -- every MLP thread passed four group barriers since.
+#pragma unroll
+        for (int l = 0; l < 4; ++l) *reinterpret_cast<float2*>(slot + ((4 * q + l) * 128 + row) * 2) = make_float2(df[2 * l], df[2 * l + 1]);
       }
       if (tm == 0) s_cnt[s] = 0;                  // the slot's previous tile was drained (free) before this one was fetched
       __syncwarp();
