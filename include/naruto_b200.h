@@ -338,7 +338,8 @@ int nrt_active_select(const float* rays_o, const float* rays_d, const float* tar
  * passes = 1 (plain TF32) or 3 (hi/lo split, ~fp32 accuracy).  d always has 128 rows. */
 /* Profiling aid: with NRT_BWD_DEBUG=8 in the environment the backward kernel stamps clock64() at its phase boundaries
  * (per CTA: entry, prologue done, MLP loop done, scatter loop done, before flush, after flush, end); this copies the
- * [256][8] int64 table to host memory (synchronises). */
+ * [256][8] int64 table to host memory (synchronises).  A NEGATIVE `bytes` reads |bytes| of the forward kernel's table instead
+ * (NRT_FWD_DEBUG=1: per CTA the cycles of sub-CTA 0 in prologue / ray staging / tiles / compositing / total / incl. statistics tail). */
 int nrt_debug_read(void* host_dst, int32_t bytes);
 int nrt_selftest_umma(int mode, const float* a, const float* b, int32_t k, int32_t n, int passes, float* d, void* stream);
 /* Raw probe: a_img / b_img (dev) are copied verbatim into shared memory and multiplied as d[128,n] with the given

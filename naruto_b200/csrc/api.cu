@@ -30,6 +30,7 @@ int64_t decode_bwd_q_scratch_floats(const NrtPlan*);
 int launch_encode_bwd(const NrtPlan*, const float*, const PointSource&, int64_t, const float*, float, float*, float*,
                       cudaStream_t);
 int q_trace_read(void*, int);
+int ws_trace_read(void*, int);
 int launch_smooth(const NrtPlan*, const float*, const float*, int, double, double, float, float*, float*, void*, int, int, cudaStream_t);
 int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
                 cudaStream_t);
@@ -486,7 +487,8 @@ int nrt_active_select(const float* rays_o, const float* rays_d, const float* tar
 }
 
 int nrt_debug_read(void* host_dst, int32_t bytes) {
-  NRT_REQUIRE(host_dst && bytes >= 0, "debug_read arguments");
+  NRT_REQUIRE(host_dst && bytes != 0, "debug_read arguments");
+  if (bytes < 0) return ws_trace_read(host_dst, -bytes);     // negative size: the forward kernel's table (NRT_FWD_DEBUG=1)
   return q_trace_read(host_dst, bytes);
 }
 

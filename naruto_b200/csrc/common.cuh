@@ -498,6 +498,7 @@ __device__ __forceinline__ void warp_sample_z(const DevPlan& P, float td, const 
     float lo[NRT_SMAX / 32], hi[NRT_SMAX / 32];
 #pragma unroll
     for (int p = 0; p < NRT_SMAX / 32; ++p) {
+      if (p * 32 >= S) break;                 // warp-uniform: rays have S <= 256 samples, the loop is unrolled for 256
       int s = p * 32 + lane;
       if (s < S) {
         float zc = z[s];
@@ -506,19 +507,26 @@ __device__ __forceinline__ void warp_sample_z(const DevPlan& P, float td, const 
       }
     }
     __syncwarp();
+    if (!u_row) {
+      // in-kernel draw: sample s takes component s & 3 of Philox(counter = (ray, s >> 2)).  One call yields four samples, so lane
+      // g evaluates the call of group g once and parks the four uniforms in z[] (free now: every lane holds its lo / hi in
+      // registers) instead of four lanes evaluating the same call to pick one component each.
+      for (int gi = lane; 4 * gi < S; gi += 32) {
+        const uint4 ctr = make_uint4((uint32_t)ray, (uint32_t)(ray >> 32), (uint32_t)gi, 0u);
+        const uint4 rnd = philox4x32(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        if (4 * gi + 0 < S) z[4 * gi + 0] = u32_to_unit(rnd.x);
+        if (4 * gi + 1 < S) z[4 * gi + 1] = u32_to_unit(rnd.y);
+        if (4 * gi + 2 < S) z[4 * gi + 2] = u32_to_unit(rnd.z);
+        if (4 * gi + 3 < S) z[4 * gi + 3] = u32_to_unit(rnd.w);
+      }
+      __syncwarp();
+    }
 #pragma unroll
     for (int p = 0; p < NRT_SMAX / 32; ++p) {
+      if (p * 32 >= S) break;                 // warp-uniform: rays have S <= 256 samples, the loop is unrolled for 256
       int s = p * 32 + lane;
       if (s < S) {
-        float r;
-        if (u_row) {
-          r = u_row[s];
-        } else {
-          uint4 ctr = make_uint4((uint32_t)ray, (uint32_t)(ray >> 32), (uint32_t)(s >> 2), 0u);
-          uint4 rnd = philox4x32(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-          uint32_t pick = (s & 3) == 0 ? rnd.x : (s & 3) == 1 ? rnd.y : (s & 3) == 2 ? rnd.z : rnd.w;
-          r = u32_to_unit(pick);
-        }
+        const float r = u_row ? u_row[s] : z[s];
         z[s] = __fadd_rn(lo[p], __fmul_rn(__fsub_rn(hi[p], lo[p]), r));
       }
     }
@@ -565,6 +573,7 @@ __device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, 
   float ws = 0.f;
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
+    if (p * 32 >= S) break;                   // warp-uniform early exit (the loop is unrolled for NRT_SMAX samples)
     const int s = p * 32 + lane;
     bw[p] = 0.f;
     zv[p] = 0.f;
@@ -580,6 +589,7 @@ __device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, 
   float c0 = 0, c1 = 0, c2 = 0, dep = 0, acc = 0, unc = 0;
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
+    if (p * 32 >= S) break;                   // warp-uniform early exit (the loop is unrolled for NRT_SMAX samples)
     const int s = p * 32 + lane;
     if (s < S) {
       const float w = zv[p] < r.z_cut ? __fdiv_rn(bw[p], denom) : 0.f;
@@ -604,6 +614,7 @@ __device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, 
   float var = 0.f;
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
+    if (p * 32 >= S) break;                   // warp-uniform early exit (the loop is unrolled for NRT_SMAX samples)
     const int s = p * 32 + lane;
     if (s < S) {
       const float dz = zv[p] - r.depth;

@@ -21,6 +21,8 @@
 // Measured and dropped for tables beyond L2 (T = 2^21, round 2): `prefetch.global.L2` of the next batch of levels by the gather
 // warps (forward 0.83 -> 0.92 ms: the prefetches cost LSU slots the loads need; at T = 2^16 0.173 -> 0.238 ms) and interleaving
 // dense and hashed levels between the two halves of a gather set (0.81 -> 0.83 ms).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "mlp_tc.cuh"
 
@@ -43,7 +45,11 @@
 // runs: the shared-memory footprint decides the L1 carve-out, and 2 KB more cost the forward 3-6 %); the partials are folded
 // per CTA at the end through the then idle ring area and reduced in CTA order by the last CTA to finish, so the result does
 // not depend on scheduling.
+// profiling aid (NRT_FWD_DEBUG=1): per-CTA cycle accounting of sub-CTA 0, read back with nrt_debug_read(which = 1)
+__device__ long long g_ws_trace[256 * 8];
+
 struct LossFuse {
+  int trace;                 // profiling aid on
   const float* target_rgb;   // NULL: statistics off
   const float* target_d;
   double* part;              // [gridDim.x][NRT_N_STATS]
@@ -98,6 +104,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
   uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + 16);
   float* sw = reinterpret_cast<float*>(smem_raw + TC_SMEM_HEADER);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const bool tr = lf.trace && blockIdx.x < 256;
+  const long long tr_t0 = tr ? clock64() : 0;
+  long long tr_stage = 0, tr_tiles = 0, tr_comp = 0, tr_pro = 0;
   if (seed_step) seed ^= (uint64_t)(uint32_t)__ldg(seed_step) * 0x9E3779B97F4A7C15ull;     // per-iteration jitter under graph replay
   if (warp == 0) {
     if (threadIdx.x == 0) {
@@ -139,6 +148,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
   c.w_lo = smem_u32(sw + FW_FLOATS);
   const bool issuer = is_mlp && (warp & 3) == 0;
 
+  if (tr) tr_pro = clock64() - tr_t0;
   const int64_t n_units = (n_rays + rpu - 1) / rpu;
   int cnt = 0;                                                        // tiles this sub-CTA has pushed through its ring
   int total_tiles = 0;                                                // ... and will have pushed at the end
@@ -150,6 +160,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
     const int64_t r0 = un * rpu;
     const int nr = (int)min((int64_t)rpu, n_rays - r0);
     const int npts = nr * S;
+    const long long tr_a = tr ? clock64() : 0;
     // ---- stage the rays and their depth samples (all 12 warps) ----
     for (int i = tsub; i < nr * 6; i += WS_SUB) {
       const int rl = i / 6, k = i - rl * 6;
@@ -165,6 +176,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
       }
     }
     bar_sync(WS_BAR_UNIT(g), WS_SUB);
+    const long long tr_b = tr ? clock64() : 0;
     // ---- tiles of 128 points ----
     if (is_mlp) {
       const int row = tsub;                                           // 0..127 = TMEM lane
@@ -273,6 +285,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
       }
     }
     bar_sync(WS_BAR_UNIT(g), WS_SUB);
+    const long long tr_c = tr ? clock64() : 0;
     // ---- integrate along each ray (all 12 warps) ----
     for (int rl = wsub; rl < nr; rl += 12) {
       const int64_t ray = r0 + rl;
@@ -343,6 +356,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
       }
     }
     bar_sync(WS_BAR_UNIT(g), WS_SUB);
+    if (tr) {
+      const long long tr_d = clock64();
+      tr_stage += tr_b - tr_a, tr_tiles += tr_c - tr_b, tr_comp += tr_d - tr_c;
+    }
+  }
+  if (tr && g == 0 && tsub == 0) {
+    long long* o = g_ws_trace + blockIdx.x * 8;
+    o[0] = tr_pro, o[1] = tr_stage, o[2] = tr_tiles, o[3] = tr_comp, o[4] = clock64() - tr_t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -393,6 +414,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) render_fwd_ws_kernel(const __gr
         if (k == 0) *lf.counter = 0u;   // re-arm for the next launch
       }
     }
+    if (tr && threadIdx.x == 0) g_ws_trace[blockIdx.x * 8 + 5] = clock64() - tr_t0;
     if (lf.losses) {                            // one shard = the whole batch: the losses follow at once (no extra launch)
       __syncthreads();
       if (*s_last && threadIdx.x == 0) {
@@ -410,6 +432,11 @@ int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float*
   if (n_rays == 0) return NRT_OK;
   const int S = plan->dev.S;
   LossFuse lf{};
+  static const int fwd_dbg = [] {
+    const char* e = getenv("NRT_FWD_DEBUG");
+    return e ? atoi(e) : 0;
+  }();
+  lf.trace = fwd_dbg;
   if (target_rgb) {          // stats buffer layout as launch_loss_partial (forward.cu): [stats(16) | counter | CTA partials]
     lf.target_rgb = target_rgb;
     lf.target_d = target_d;
@@ -441,5 +468,11 @@ int launch_render_fwd_ws(const NrtPlan* plan, const NrtParams* prm, const float*
     render_fwd_ws_kernel<false><<<blocks, WS_THREADS, smem, st>>>(plan->dev, *prm, rays_o, rays_d, target_d, n_rays, z_in, u, perturb,
                                                                  seed, seed_step, (int)rpu, *out, lf);
   NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
+
+int ws_trace_read(void* dst, int bytes) {
+  const int a = (int)sizeof(long long) * 256 * 8;
+  NRT_CUDA_CHECK(cudaMemcpyFromSymbol(dst, g_ws_trace, bytes < a ? bytes : a));
   return NRT_OK;
 }
