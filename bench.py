@@ -461,18 +461,25 @@ def run_ours(args):
         kern = {k: {'ms': round(v[0], 4), 'algorithmic_GB_per_s': round(v[1] / v[0] / 1e6, 1)} for k, v in kt.items()}
         top = max(kt, key=lambda k: kt[k][0])
         ach = kt[top][1] / kt[top][0] / 1e6
-        traffic = None
+        traffic, lsu = None, None
         tj = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tj):
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (same workload)
-            tr = json.load(open(tj))['dram_bytes_per_launch']
+            tjd = json.load(open(tj))
+            tr = tjd['dram_bytes_per_launch']
             traffic = tr.get('decode_bwd_q_kernel' if 'bwd' in top else 'render_fwd_ws_kernel')
+            lsu = tjd.get('decode_bwd_q_kernel_lsu') if 'bwd' in top else None
         roof = {'bound': 'hbm', 'kernel': top, 'achieved': round(ach, 1), 'peak': hbm, 'unit': 'GB/s', 'frac': round(ach / hbm, 4),
                 'traffic': traffic, 'peak_source': how,
                 'note': 'algorithmic bytes (SURVEY 8d) / CUDA-event time of the kernel launched alone, L2 flushed; at hash_size 16 '
                         'the 6.5 MB table is L2-resident so the gather fraction is an accounting convention; the backward entry '
                         'is the launches of nrt_render_bwd: composite_bwd_kernel (7% of it) + decode_bwd_q_kernel + wgrad_reduce_kernel; traffic is '
                         'decode_bwd_q_kernel\'s',
+                'lsu_floor': None if not lsu else {
+                    'what': 'what actually bounds decode_bwd_q: the SM load/store pipe.  A no-return reduction costs 0.79 ns per lane per SM '
+                            'whatever its width (tools/micro/red_throughput.cu); lanes / shared wavefronts / shuffles from the committed ncu capture',
+                    'red_lane_floor_ms': round(lsu['red_lanes_per_launch'] * lsu['red_ns_per_lane_per_sm'] * 1e-6 / 148, 4),
+                    'red_lanes_per_launch': lsu['red_lanes_per_launch'], 'shared_wavefronts_per_launch': lsu['shared_wavefronts_per_launch']},
                 'hash_gather': {'kernel': 'render_fwd_ws_kernel', 'achieved': kern['render_fwd_ws_kernel']['algorithmic_GB_per_s'],
                                 'frac': round(kern['render_fwd_ws_kernel']['algorithmic_GB_per_s'] / hbm, 4)}}
     sweep = None
