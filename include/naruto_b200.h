@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define NRT_ABI_VERSION 3
+#define NRT_ABI_VERSION 4
 
 typedef enum NrtStatus {
   NRT_OK = 0,
@@ -293,6 +293,16 @@ int nrt_stats_exchange(const NrtPeerTable* peers, double* stats, uint32_t* xchg,
  * done_counter: dev u32 scratch, zero-filled once.  Returns after every rank's stores are visible everywhere. */
 int nrt_adam_step_peers(const NrtPeerTable* peers, float* exp_avg, float* exp_avg_sq, const NrtAdamGroup* groups, int32_t n_groups,
                         int64_t smooth_slot, float* smooth_total, const uint32_t* xchg, uint32_t* done_counter, void* stream);
+
+/* The same three groups on ONE rank in one launch (torch.optim.Adam.step() + zero_grad() of create_optimizer's two groups,
+ * src/slam/coslam/coslam.py:409-419, and of init_uncert_grid_optim's, :240-243): param / grad / exp_avg / exp_avg_sq are the
+ * flat vectors [grid | w1 | w2 | w3 | w4 | uncert] (dev fp32, 16-byte aligned), groups as above (float ranges; begin a
+ * multiple of 4, any end), a disabled group is left untouched.  Same arithmetic as nrt_adam_step. */
+int nrt_adam_step_groups(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const NrtAdamGroup* groups, int32_t n_groups,
+                         int zero_grad, void* stream);
+/* nrt_step_begin(map_counter, 1, ...) that also advances a second counter by one when it is given (the uncertainty grid's
+ * Adam step count, on the iterations that step it): one launch opens the iteration. */
+int nrt_iteration_begin(int32_t* map_counter_dev, int32_t* uncert_counter_dev, uint64_t seed, float* rand6_dev, void* stream);
 
 /* ---- device-resident ray sampling ----------------------------------------------------------------
  * The host half of the mapping iteration on device-resident data.  Index lists are dev int64

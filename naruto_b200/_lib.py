@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libnaruto_b200.so')
 
-NRT_ABI_VERSION = 3
+NRT_ABI_VERSION = 4
 N_LOSS = 8
 N_STATS = 16
 N_STATS_SUM = 11
@@ -73,6 +73,7 @@ SIGNATURES = {
     'nrt_render_fwd_stats': (C.c_int, [_P, C.POINTER(NrtParams), c_fp, c_fp, c_fp, c_fp, C.c_int64, c_fp, C.c_int, C.c_uint64,
                                        c_fp, C.POINTER(NrtRenderOut), c_fp, c_fp, _P]),
     'nrt_step_begin': (C.c_int, [c_fp, C.c_int32, C.c_uint64, c_fp, _P]),
+    'nrt_iteration_begin': (C.c_int, [c_fp, c_fp, C.c_uint64, c_fp, _P]),
     'nrt_mc_workspace_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     'nrt_mc_extract': (C.c_int, [c_fp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, c_fp, _P, C.POINTER(C.c_void_p)]),
     'nrt_mc_result_sizes': (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -84,6 +85,7 @@ SIGNATURES = {
     'nrt_erp_depth2dist_analytic': (C.c_int, [c_fp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_float, c_fp, _P]),
     'nrt_debug_read': (C.c_int, [C.c_void_p, C.c_int32]),
     'nrt_stats_exchange': (C.c_int, [C.POINTER(NrtPeerTable), c_fp, c_fp, c_fp, _P]),
+    'nrt_adam_step_groups': (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.POINTER(NrtAdamGroup), C.c_int32, C.c_int, _P]),
     'nrt_adam_step_peers': (C.c_int, [C.POINTER(NrtPeerTable), c_fp, c_fp, C.POINTER(NrtAdamGroup), C.c_int32, C.c_int64, c_fp, c_fp, c_fp,
                                      _P]),
     'nrt_loss_stats_bytes': (C.c_int64, []),

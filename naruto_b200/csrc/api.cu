@@ -35,7 +35,8 @@ int launch_smooth(const NrtPlan*, const float*, const float*, int, double, doubl
 int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
                 cudaStream_t);
 int launch_counter_add(int*, int, cudaStream_t);
-int launch_step_begin(int*, int, uint64_t, float*, cudaStream_t);
+int launch_step_begin(int*, int, uint64_t, float*, int*, cudaStream_t);
+int launch_adam_groups(float*, float*, float*, float*, const NrtAdamGroup*, int, int, int, cudaStream_t);
 int launch_map_volumes(const NrtPlan*, const NrtParams*, const int*, float*, float*, cudaStream_t);
 int64_t mc_workspace_bytes(int, int, int);
 int mc_extract(const float*, int, int, int, float, float, void*, cudaStream_t, void**);
@@ -419,7 +420,23 @@ int nrt_adam_step_peers(const NrtPeerTable* peers, float* exp_avg, float* exp_av
 
 int nrt_step_begin(int32_t* counter_dev, int32_t delta, uint64_t seed, float* rand6_dev, void* stream) {
   NRT_REQUIRE(counter_dev, "null counter");
-  return launch_step_begin(counter_dev, delta, seed, rand6_dev, (cudaStream_t)stream);
+  return launch_step_begin(counter_dev, delta, seed, rand6_dev, nullptr, (cudaStream_t)stream);
+}
+
+int nrt_iteration_begin(int32_t* map_counter_dev, int32_t* uncert_counter_dev, uint64_t seed, float* rand6_dev, void* stream) {
+  NRT_REQUIRE(map_counter_dev, "null counter");
+  return launch_step_begin(map_counter_dev, 1, seed, rand6_dev, uncert_counter_dev, (cudaStream_t)stream);
+}
+
+int nrt_adam_step_groups(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const NrtAdamGroup* groups, int32_t n_groups,
+                         int zero_grad, void* stream) {
+  NRT_REQUIRE(param && grad && exp_avg && exp_avg_sq && groups && n_groups >= 1 && n_groups <= 3, "adam_step_groups arguments");
+  NRT_REQUIRE(((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0,
+              "adam_step_groups: the flat vectors must be 16-byte aligned");
+  for (int i = 0; i < n_groups; ++i)
+    NRT_REQUIRE(groups[i].begin % 4 == 0 && groups[i].end >= groups[i].begin && (groups[i].step_dev || !groups[i].enabled),
+                "adam group: begin a multiple of 4 floats, step counter on the device");
+  return launch_adam_groups(param, grad, exp_avg, exp_avg_sq, groups, n_groups, zero_grad, nrt_device_sm_count(), (cudaStream_t)stream);
 }
 
 int nrt_counter_add(int32_t* counter_dev, int32_t delta, void* stream) {

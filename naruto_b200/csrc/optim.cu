@@ -116,6 +116,9 @@ int launch_smooth(const NrtPlan* plan, const float* grid, const float* rnd6, int
   const int64_t lo = pts * part / n_parts, hi = pts * (part + 1) / n_parts;      // this part's slab of the scan order
   float2* F = reinterpret_cast<float2*>(workspace);
   LatticeSpec ls{n, (float)voxel, (float)((double)(n - 1) * voxel), (float)margin, (float)(2.0 * margin)};
+  // The accumulator is cleared by a memset node, not by the first kernel: on the forked branch of the mapping iteration
+  // (mapper.py) that node also lets the ray path's next kernel take its SMs first -- measured 205 -> 187 us per iteration at
+  // 2048 rays x 43 samples against clearing it inside smooth_encode_kernel (profiles/r02d_smooth_branch.log).
   NRT_CUDA_CHECK(cudaMemsetAsync(loss, 0, sizeof(float), st));
   smooth_encode_kernel<<<blocks, 256, 0, st>>>(plan->dev, (const float2*)grid, rnd6, ls, F);
   NRT_CUDA_CHECK(cudaGetLastError());
@@ -158,6 +161,86 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   }
 }
 
+// All parameter groups of the scene model in ONE launch (create_optimizer's two groups + the uncertainty grid's own Adam):
+// the groups are ranges of the flat [grid | decoder | uncert] vectors; a disabled group (the uncertainty grid on four
+// iterations out of five) is skipped and keeps accumulating its gradient.  Same arithmetic as adam_kernel.
+struct AdamRange {
+  int64_t begin, end;            // floats; begin is a multiple of 4
+  float lr, beta1, beta2, eps, wd;
+  const int* step_dev;
+  int enabled;
+};
+
+__device__ __forceinline__ void adam_bias_terms(const AdamRange& R, float* out) {
+  const int st = R.enabled ? *R.step_dev : 1;
+  const double bc1 = 1.0 - pow((double)R.beta1, (double)st), bc2 = 1.0 - pow((double)R.beta2, (double)st);
+  out[0] = (float)((double)R.lr / bc1);          // step_size
+  out[1] = (float)sqrt(bc2);                     // bias_correction2_sqrt
+}
+
+__device__ __forceinline__ void adam_range(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                           const AdamRange& R, float step_size, float bc2s, int zero_grad) {
+  const float beta2 = R.beta2, eps = R.eps, wd = R.wd, omb1 = 1.0f - R.beta1, omb2 = 1.0f - R.beta2;
+  auto one = [&](float& pi, float gi, float& mi, float& vi) {
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    mi = mi + (gi - mi) * omb1;
+    vi = vi * beta2 + omb2 * gi * gi;
+    const float denom = sqrtf(vi) / bc2s + eps;
+    pi = pi - step_size * (mi / denom);
+  };
+  const int t = threadIdx.x;
+  const int64_t b4 = R.begin >> 2, e4 = R.end >> 2;                 // whole float4s, then a scalar tail
+  for (int64_t i = b4 + (int64_t)blockIdx.x * blockDim.x + t; i < e4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pi = reinterpret_cast<float4*>(p)[i], mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    one(pi.x, gv.x, mi.x, vi.x);
+    one(pi.y, gv.y, mi.y, vi.y);
+    one(pi.z, gv.z, mi.z, vi.z);
+    one(pi.w, gv.w, mi.w, vi.w);
+    reinterpret_cast<float4*>(p)[i] = pi;
+    reinterpret_cast<float4*>(m)[i] = mi;
+    reinterpret_cast<float4*>(v)[i] = vi;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (blockIdx.x == 0) {
+    const int64_t i = (e4 << 2) + t;
+    if (i < R.end) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      one(pi, g[i], mi, vi);
+      p[i] = pi, m[i] = mi, v[i] = vi;
+      if (zero_grad) g[i] = 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) adam_groups_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                          float* __restrict__ v, const __grid_constant__ AdamRange r0,
+                                                          const __grid_constant__ AdamRange r1, const __grid_constant__ AdamRange r2,
+                                                          int zero_grad) {
+  __shared__ float s_c[3][2];
+  const int t = threadIdx.x;
+  if (t == 0) adam_bias_terms(r0, s_c[0]);
+  if (t == 32) adam_bias_terms(r1, s_c[1]);
+  if (t == 64) adam_bias_terms(r2, s_c[2]);
+  __syncthreads();
+  if (r0.enabled) adam_range(p, g, m, v, r0, s_c[0][0], s_c[0][1], zero_grad);
+  if (r1.enabled) adam_range(p, g, m, v, r1, s_c[1][0], s_c[1][1], zero_grad);
+  if (r2.enabled) adam_range(p, g, m, v, r2, s_c[2][0], s_c[2][1], zero_grad);
+}
+
+int launch_adam_groups(float* p, float* g, float* m, float* v, const NrtAdamGroup* groups, int n_groups, int zero_grad, int sm_count,
+                       cudaStream_t st) {
+  AdamRange r[3] = {};
+  for (int i = 0; i < n_groups && i < 3; ++i) {
+    r[i].begin = groups[i].begin, r[i].end = groups[i].end;
+    r[i].lr = groups[i].lr, r[i].beta1 = groups[i].beta1, r[i].beta2 = groups[i].beta2, r[i].eps = groups[i].eps;
+    r[i].wd = groups[i].weight_decay, r[i].step_dev = groups[i].step_dev, r[i].enabled = groups[i].enabled;
+  }
+  adam_groups_kernel<<<sm_count * 8, 256, 0, st>>>(p, g, m, v, r[0], r[1], r[2], zero_grad);
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
+}
+
 __global__ void counter_add_kernel(int* c, int delta) {
   if (threadIdx.x == 0 && blockIdx.x == 0) *c += delta;
 }
@@ -176,10 +259,11 @@ int launch_adam(float* p, float* g, float* m, float* v, int64_t n, int step, con
 // Start of a mapping iteration inside a replayed CUDA graph: advance the device-side step counter and draw the six uniforms
 // of the smoothness lattice (torch.rand(3), torch.rand((1,1,1,3)) in tp/coslam.py:252-258) from Philox keyed by (seed, step),
 // so no host value and no separate RNG launch is needed per iteration.
-__global__ void step_begin_kernel(int* c, int delta, uint64_t seed, float* __restrict__ rand6) {
+__global__ void step_begin_kernel(int* c, int delta, uint64_t seed, float* __restrict__ rand6, int* c2) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int step = *c + delta;
   *c = step;
+  if (c2) *c2 += 1;            // second counter (the uncertainty grid's Adam step on the iterations that step it)
   if (rand6) {
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const uint4 a = philox4x32(make_uint4((uint32_t)step, 0x534d4f4fu, 0u, 0u), key);
@@ -193,8 +277,8 @@ __global__ void step_begin_kernel(int* c, int delta, uint64_t seed, float* __res
   }
 }
 
-int launch_step_begin(int* c, int delta, uint64_t seed, float* rand6, cudaStream_t st) {
-  step_begin_kernel<<<1, 32, 0, st>>>(c, delta, seed, rand6);
+int launch_step_begin(int* c, int delta, uint64_t seed, float* rand6, int* c2, cudaStream_t st) {
+  step_begin_kernel<<<1, 32, 0, st>>>(c, delta, seed, rand6, c2);
   NRT_CUDA_CHECK(cudaGetLastError());
   return NRT_OK;
 }

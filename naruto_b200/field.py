@@ -274,6 +274,19 @@ class FieldPlan:
         L.check(self.lib.nrt_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), int(step), L.ptr(step_dev), lr, beta1,
                                        beta2, eps, weight_decay, int(zero_grad), _stream()))
 
+    def adam_step_groups(self, theta, grad, exp_avg, exp_avg_sq, groups, zero_grad=True):
+        """groups: list of (begin, end, lr, beta1, beta2, eps, weight_decay, step_dev tensor, enabled) over the flat vectors."""
+        arr = (L.NrtAdamGroup * len(groups))()
+        for a, (b, e, lr, b1, b2, eps, wd, step_dev, en) in zip(arr, groups):
+            a.begin, a.end, a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = b, e, lr, b1, b2, eps, wd
+            a.step_dev, a.enabled = L.ptr(step_dev), int(en)
+        L.check(self.lib.nrt_adam_step_groups(L.ptr(theta), L.ptr(grad), L.ptr(exp_avg), L.ptr(exp_avg_sq), arr, len(groups),
+                                              int(zero_grad), _stream()))
+
+    def iteration_begin(self, map_counter, uncert_counter=None, seed=0, rand6=None):
+        L.check(self.lib.nrt_iteration_begin(L.ptr(map_counter), L.ptr(uncert_counter) if uncert_counter is not None else None,
+                                             int(seed), L.ptr(rand6) if rand6 is not None else None, _stream()))
+
     def step_begin(self, counter, seed=0, rand6=None, delta=1):
         L.check(self.lib.nrt_step_begin(L.ptr(counter), int(delta), int(seed), L.ptr(rand6) if rand6 is not None else None, _stream()))
 

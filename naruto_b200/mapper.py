@@ -216,6 +216,14 @@ class MappingStep:
         self.base_seed = 0x9E3779B9
         self.seed = self.base_seed + 7919 * self.rank
         self._graphs = {}
+        # The ray-independent smoothness term runs on a forked branch of the iteration, joined before the optimiser step
+        # (NRT_SMOOTH_FORK: 0 in line, 1 forked after the iteration's first launch, 2 forked after the render forward).
+        # Measured on B200 (profiles/r02d_smooth_branch.log), iteration in us for fork 0 / 1 / 2: 4096 rays x 128 samples
+        # 449 / 426 / 433; 2048 x 43: 213 / 203 / 187 -- long forwards hide it best under their own tail, short ones under
+        # the backward's start.
+        fork = os.environ.get('NRT_SMOOTH_FORK')
+        self.smooth_fork = int(fork) if fork is not None else (1 if n_rays * plan.S >= (1 << 18) else 2)
+        self._branch = None
         self.launches_per_iter = {False: 0, True: 0}
 
     # -------------------------------------------------------------------------------------------
@@ -224,6 +232,7 @@ class MappingStep:
         p, n = self.plan, 0
         smooth = self.smooth_on if smooth is None else (bool(smooth) and self.smooth_w > 0)
         fused_losses = self.losses if self.world == 1 else None      # one shard: the render kernel's last CTA finalizes the losses
+        forked = False
         if self.external_random:                            # test hook: caller-written self.u / self.rand6 (the reference's draws)
             p.counter_add(self.map_step, 1); n += 1
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=self.u,
@@ -231,45 +240,62 @@ class MappingStep:
         else:
             # the reference's torch.rand(z_vals.shape), torch.rand(3), torch.rand((1,1,1,3)) draws, made on the device from Philox
             # keyed by (seed, step counter): nothing host-side changes between graph replays
-            p.step_begin(self.map_step, self.base_seed, self.rand6 if smooth else None); n += 1
+            p.iteration_begin(self.map_step, self.unc_step if with_uncert_step else None, self.base_seed,
+                              self.rand6 if smooth else None); n += 1
+            if smooth and self.smooth_fork == 1:
+                n += self._smooth_branch(); forked = True
+            ev = torch.cuda.current_stream().record_event() if smooth and self.smooth_fork == 3 else None
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=None,
                                seed=self.seed, seed_step=self.map_step, losses=fused_losses); n += 1
+            if ev is not None:                              # forked before the forward, launched after it
+                n += self._smooth_branch(ev); forked = True
         if fused_losses is None:                            # N > 1: the losses are ratios of GLOBAL sums
             if self.peers is not None:                      # exchange + finalize in one launch over peer memory
                 self.peers.stats_exchange(self.stats, self.losses); n += 1
             else:
                 reduce_stats(self.stats, self.pg)
                 p.loss_finalize(self.stats, self.losses); n += 1
+        if smooth and self.smooth_fork == 2:
+            n += self._smooth_branch(); forked = True
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,
                      self.G, workspace=self.ws_bwd); n += 3     # composite_bwd, decode_bwd_q, wgrad_reduce
-        if smooth:                                          # ray-independent term: every rank takes one slab of the lattice
+        if smooth and not forked:                           # ray-independent term: every rank takes one slab of the lattice
             p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
                              self.smooth_loss, self.G.grid, self.ws_smooth, part=self.rank, n_parts=self.world); n += 2
+        elif forked:
+            torch.cuda.current_stream().wait_stream(self._branch)      # join: the optimiser needs both gradients
         ng, nd = self.n_grid, self.n_dec
+        if with_uncert_step and self.external_random:       # (otherwise iteration_begin advanced the uncertainty step counter)
+            p.counter_add(self.unc_step, 1); n += 1
+        # create_optimizer (src/slam/coslam/coslam.py:409-419): grid group eps=1e-15, decoder group wd=1e-6, betas (0.9,0.99);
+        # init_uncert_grid_optim (:240-243): Adam(lr=1), stepped and zeroed every 5th iteration (:397-399) -- in between the
+        # uncertainty-grid gradient keeps accumulating
+        groups = [(0, ng, self.lr_embed, 0.9, 0.99, 1e-15, 0.0, self.map_step, True),
+                  (ng, ng + nd, self.lr_decoder, 0.9, 0.99, 1e-8, 1e-6, self.map_step, True),
+                  (ng + nd, ng + nd + self.n_unc, 1.0, 0.9, 0.999, 1e-8, 0.0, self.unc_step, bool(with_uncert_step))]
         if self.peers is not None:
             # reduce-scatter + Adam (all three groups) + all-gather in ONE launch over peer memory (csrc/peer.cu)
-            if with_uncert_step:
-                p.counter_add(self.unc_step, 1); n += 1
-            self.peers.adam_step(self.exp_avg, self.exp_avg_sq, [
-                (0, ng, self.lr_embed, 0.9, 0.99, 1e-15, 0.0, self.map_step, True),
-                (ng, ng + nd, self.lr_decoder, 0.9, 0.99, 1e-8, 1e-6, self.map_step, True),
-                (ng + nd, ng + nd + self.n_unc, 1.0, 0.9, 0.999, 1e-8, 0.0, self.unc_step, bool(with_uncert_step))],
-                self.smooth_total if smooth else None); n += 1
+            self.peers.adam_step(self.exp_avg, self.exp_avg_sq, groups, self.smooth_total if smooth else None); n += 1
             return n
         reduce_grads(self.bucket, self.pg)
-        # create_optimizer (src/slam/coslam/coslam.py:409-419): decoder group wd=1e-6, grid group eps=1e-15, betas (0.9,0.99)
-        p.adam_step(self.theta[:ng], self.grad[:ng], self.exp_avg[:ng], self.exp_avg_sq[:ng], 0, self.lr_embed, 0.9, 0.99,
-                    1e-15, 0.0, zero_grad=True, step_dev=self.map_step); n += 1
-        p.adam_step(self.theta[ng:ng + nd], self.grad[ng:ng + nd], self.exp_avg[ng:ng + nd], self.exp_avg_sq[ng:ng + nd], 0,
-                    self.lr_decoder, 0.9, 0.99, 1e-8, 1e-6, zero_grad=True, step_dev=self.map_step); n += 1
-        if with_uncert_step:
-            # init_uncert_grid_optim (:240-243): Adam(lr=1), stepped and zeroed every 5th iteration (:397-399);
-            # in between the uncertainty-grid gradient keeps accumulating
-            o = ng + nd
-            p.counter_add(self.unc_step, 1); n += 1
-            p.adam_step(self.theta[o:], self.grad[o:], self.exp_avg[o:], self.exp_avg_sq[o:], 0, 1.0, 0.9, 0.999, 1e-8, 0.0,
-                        zero_grad=True, step_dev=self.unc_step); n += 1
+        p.adam_step_groups(self.theta, self.grad, self.exp_avg, self.exp_avg_sq, groups, zero_grad=True); n += 1
         return n
+
+    def _smooth_branch(self, after=None):
+        """Launch the smoothness term on a second stream forked off the current one (inside a capture this becomes a parallel
+        branch of the graph): it reads the parameters and rand6 and adds into the table gradient with reductions, so it only
+        has to be ordered before the optimiser step."""
+        p = self.plan
+        if self._branch is None:
+            self._branch = torch.cuda.Stream(device=self.dev)
+        if after is None:
+            self._branch.wait_stream(torch.cuda.current_stream())
+        else:
+            self._branch.wait_event(after)
+        with torch.cuda.stream(self._branch):
+            p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
+                             self.smooth_loss, self.G.grid, self.ws_smooth, part=self.rank, n_parts=self.world)
+        return 2
 
     def _graph(self, with_uncert_step, smooth=None):
         smooth = self.smooth_on if smooth is None else (bool(smooth) and self.smooth_w > 0)
@@ -285,7 +311,8 @@ class MappingStep:
             for b, s in zip(self.state.persistent(), saved):
                 b.copy_(s)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            cap = torch.cuda.Stream(device=self.dev, priority=-1) if os.environ.get('NRT_MAIN_PRIO') == '1' else None
+            with torch.cuda.graph(g, stream=cap):
                 self.launches_per_iter[bool(with_uncert_step)] = self._body(with_uncert_step, smooth)
             for b, s in zip(self.state.persistent(), saved):
                 b.copy_(s)

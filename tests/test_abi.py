@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f'{n} declared in include/naruto_b200.h but not exported'
     assert sorted(_lib.SIGNATURES) == names, 'ctypes signatures and header disagree'
-    assert lib.nrt_abi_version() == _lib.NRT_ABI_VERSION == 3
+    assert lib.nrt_abi_version() == _lib.NRT_ABI_VERSION == 4
 
 
 def test_plan_level_table_matches_oracle(spec):

@@ -1,5 +1,11 @@
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2x_tests.log 2>&1; tail -3 gpurun_out/r2x_tests.log
-for i in 1 2; do timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-torch-gpu-baseline --no-dropin --sweep-rays 0 2>/dev/null | python -c "
-import json,sys;d=json.loads(sys.stdin.read());print(d['ms_per_step'],d['kernels'],{k:(v['ms_per_step'],v.get('fwd_ms')) for k,v in d['configs'].items()})"; done
-NRT_FWD_DEBUG=1 python tools/probe_fwd.py 4096 117 2>&1 | head -7
-NRT_FWD_DEBUG=1 python tools/probe_fwd.py 2148 32 2>&1 | head -7
+mkdir -p gpurun_out
+python -m pytest tests -x -q -m gpu > gpurun_out/r3d_tests.log 2>&1; tail -3 gpurun_out/r3d_tests.log
+python bench.py > gpurun_out/r3d_bench.json 2> gpurun_out/r3d_bench.err; tail -c 600 gpurun_out/r3d_bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r3d_bench.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e'], d['gpu_launches'])
+print(d['kernels']); print(d['sweep']['ms'], d['sweep']['frac_of_hbm_peak'])
+for k,v in d['configs'].items(): print(k, v['ms_per_step'], v.get('fwd_ms'))
+print(d.get('e2e_dropin'))
+PY
