@@ -349,6 +349,80 @@ def dropin_path(cfg, bound, init, host_batches, B, dev, torch, flush, steps, war
                     '(the one-import swap; no CUDA graph, Python optimiser)'}
 
 
+def mapper_path(dev, torch, n_calls=6, n_keyframes=24):
+    """The Mapper-level drop-in, timed end to end: `global_BA(slam, batch, cur_frame_id)` of
+    naruto_b200/coslam_mapper.py = src/slam/coslam/coslam.py:246-407 as shipped for Replica office_0 (mapping.sample 2048,
+    iters 10, 32+11 samples/ray, active ray sampling, filter_depth) on a duck-typed CoSLAMNaruto whose key-frame database
+    holds `n_keyframes` 680x1200 frames (past 20 key frames the batch size no longer changes from call to call: the steady
+    state of a run; before that every new size runs un-captured, see FusedMapper.step_for).  `batch` is what the reference's data loader hands over: HOST tensors; the timed
+    region of a call holds the H2D copy of the frame, the per-iteration device-side sampling (key-frame + current-frame draws,
+    pose application, uncertainty-guided selection), 10 fused mapping iterations and the D2H read of the loss."""
+    import contextlib
+    import io
+    import types
+    from naruto_b200 import coslam_mapper as cm
+    from naruto_b200.configs import replica_office0, OFFICE0_BOUND
+    from naruto_b200.ray_sampler import DeviceActiveRaySampler, DeviceKeyFrameDatabase
+    from naruto_b200.scene_rep import JointEncodingNaruto
+    from naruto_b200.synthetic import SyntheticFrame, camera_rays
+    cfg = replica_office0()
+    cfg['mapping']['active_ray'] = True
+    H, W = 680, 1200
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = JointEncodingNaruto(cfg, torch.tensor(OFFICE0_BOUND)).to(dev)
+    map_opt = torch.optim.Adam([{'params': m.decoder.parameters(), 'weight_decay': 1e-6, 'lr': cfg['mapping']['lr_decoder']},
+                                {'params': m.embed_fn.parameters(), 'eps': 1e-15, 'lr': cfg['mapping']['lr_embed']}], betas=(0.9, 0.99))
+    unc_opt = torch.optim.Adam(params=[m.get_uncert_grid(0.1)], lr=1)
+    s = types.SimpleNamespace(config=cfg, model=m, map_optimizer=map_opt, uncert_optim=unc_opt, device=dev,
+                              dataset=types.SimpleNamespace(H=H, W=W), est_c2w_data={}, est_c2w_data_rel={}, step=0,
+                              info_printer=lambda *a, **k: None)
+    n_save = int(H * W * cfg['mapping']['n_pixels'])
+    every = cfg['mapping']['keyframe_every']
+    s.keyframeDatabase = DeviceKeyFrameDatabase(cfg, H, W, n_keyframes + n_calls + 4, n_save, dev)
+    s.active_ray_sampler = DeviceActiveRaySampler(config=cfg, num_uncert_sample=500, oversample_mul=4)
+    s.cached_uncert = torch.rand(*m.plan.uncert_dims, device=dev)
+    dirs = camera_rays(H, W)
+
+    def frame(fid):
+        f = SyntheticFrame(OFFICE0_BOUND, seed=900 + fid, H=H, W=W)
+        s.est_c2w_data[fid] = f.c2w.to(dev)
+        return {'frame_id': torch.tensor([fid]), 'c2w': f.c2w.unsqueeze(0), 'rgb': f.rgb.reshape(1, H, W, 3),
+                'depth': f.depth.reshape(1, H, W), 'direction': dirs.unsqueeze(0)}
+
+    for k in range(n_keyframes):
+        s.keyframeDatabase.add_keyframe(frame(k * every), filter_depth=cfg['mapping']['filter_depth'])
+    ts, loss = [], None
+    iters = cfg['mapping']['iters']
+    for c in range(n_calls + 3):
+        fid = (n_keyframes + c) * every
+        batch = frame(fid)
+        torch.cuda.synchronize()
+        prof = None
+        if os.environ.get('NRT_PROFILE_MAPPER') and c == n_calls + 2:      # host-side profile of the last call -> stderr
+            import cProfile
+            prof = cProfile.Profile()
+            prof.enable()
+        t0 = time.perf_counter()
+        out = cm.global_BA(s, batch, fid)
+        loss = out[1].item()                        # D2H of the call's result
+        ts.append(time.perf_counter() - t0)
+        if prof is not None:
+            import pstats
+            prof.disable()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats('cumulative').print_stats(45)
+        s.keyframeDatabase.add_keyframe(batch, filter_depth=cfg['mapping']['filter_depth'])
+    ts = ts[3:]                                     # the first call of a batch size runs eagerly, the second builds the graphs
+    tsec = sum(ts) / len(ts)
+    fm = cm._mapper(s)
+    rays = max(fm.steps) if fm.steps else cfg['mapping']['sample']       # mapping.sample + the current-frame tail
+    fm.release()
+    return {'what': 'coslam_mapper.global_BA on HOST frames: H2D of the 680x1200 frame + device-side sampling + '
+                    f'{iters} fused mapping iterations + D2H of the loss, per call (wall clock, synchronised)',
+            'ms_per_call': round(1e3 * tsec, 3), 'iterations_per_call': iters, 'rays_per_iteration': rays,
+            'key_frames': n_keyframes, 'value': rays * iters / tsec, 'unit': UNIT, 'finite': bool(loss == loss),
+            'h2d_bytes_per_call': H * W * 7 * 4, 'd2h_bytes_per_call': 4}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -521,6 +595,12 @@ def run_ours(args):
             dropin = dropin_path(cfg, OFFICE0_BOUND, init, host_batches, B, dev, torch, flush, min(K, 20), 5)
         except Exception as e:
             dropin = {'error': repr(e)[:300]}
+    mapper = None
+    if rank == 0 and world == 1 and args.dropin:
+        try:
+            mapper = mapper_path(dev, torch)
+        except Exception as e:
+            mapper = {'error': repr(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_cpu, k_cpu = 1024, 5
         tot, threads = cpu_reference(n_cpu, k_cpu, 1)
@@ -569,6 +649,8 @@ def run_ours(args):
         line['cpu_baseline'] = cpu
     if dropin is not None:
         line['e2e_dropin'] = dropin
+    if mapper is not None:
+        line['e2e_mapper'] = mapper
     if side is not None:
         line['configs'] = side
     print(json.dumps(line))

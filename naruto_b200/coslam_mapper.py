@@ -45,17 +45,28 @@ class FusedMapper:
         self.state = FusedState(self.plan, self.dev)
         self.state.bind_model(model, getattr(slam, 'map_optimizer', None), getattr(slam, 'uncert_optim', None))
         self.steps = {}
+        self.uses = {}
         self._seed = 0
 
-    def step_for(self, n_rays):
+    def step_for(self, n_rays, n_iters=0):
+        """The MappingStep of this batch size.  While the key-frame database fills up (its first ~20 frames) the batch size
+        changes from call to call (the current-frame share is sample // n_keyframes): a size met for the first time runs its
+        iterations as plain launches, and only a size that comes back is captured into CUDA graphs -- a capture costs about as
+        much as 20 eager iterations."""
         n_rays = int(n_rays)
         if n_rays not in self.steps:
             if len(self.steps) >= 8:                       # early key frames change the batch size a few times; keep memory bounded
                 old = next(iter(self.steps))
                 self.steps.pop(old).release_graphs()
+                self.uses.pop(old, None)
             self.steps[n_rays] = MappingStep(self.plan, self.cfg, n_rays, self.dev, process_group=self.pg,
-                                             use_graph=self.use_graph, state=self.state)
-        return self.steps[n_rays]
+                                             use_graph=False, state=self.state)
+            self.uses[n_rays] = 0
+        self.uses[n_rays] += 1
+        ms = self.steps[n_rays]
+        if self.use_graph and (self.uses[n_rays] >= 2 or n_iters >= 40):      # (first_frame_mapping: 200 iterations of one size)
+            ms.use_graph = True
+        return ms
 
     def next_seed(self):
         self._seed += 1
@@ -106,7 +117,7 @@ def first_frame_mapping(slam, batch, n_iters=100, indices=None):
     H, W, n = slam.dataset.H, slam.dataset.W, int(cfg['mapping']['sample'])
     frame = pack_frame(batch['direction'].squeeze(0).to(dev), batch['rgb'].squeeze(0).to(dev), batch['depth'].squeeze(0).to(dev))
     poses = c2w.reshape(1, 4, 4).float().contiguous()
-    ms = fm.step_for(n)
+    ms = fm.step_for(n, n_iters)
     if cfg['decoder']['uncert_grid']:
         ms.zero_uncert_grad()                                  # self.uncert_optim.zero_grad()
     empty = torch.empty(0, dtype=torch.int64, device=dev)

@@ -217,12 +217,13 @@ class MappingStep:
         self.seed = self.base_seed + 7919 * self.rank
         self._graphs = {}
         # The ray-independent smoothness term runs on a forked branch of the iteration, joined before the optimiser step
-        # (NRT_SMOOTH_FORK: 0 in line, 1 forked after the iteration's first launch, 2 forked after the render forward).
-        # Measured on B200 (profiles/r02d_smooth_branch.log), iteration in us for fork 0 / 1 / 2: 4096 rays x 128 samples
-        # 449 / 426 / 433; 2048 x 43: 213 / 203 / 187 -- long forwards hide it best under their own tail, short ones under
-        # the backward's start.
-        fork = os.environ.get('NRT_SMOOTH_FORK')
-        self.smooth_fork = int(fork) if fork is not None else (1 if n_rays * plan.S >= (1 << 18) else 2)
+        # (NRT_SMOOTH_FORK: 0 in line, 1 forked after the iteration's first launch, 2 forked after the render forward), held
+        # back by NRT_SMOOTH_STAGGER one-block launches so that the ray path's next kernel (composite_bwd) is resident first
+        # and the lattice kernels fill in around it.  Measured on B200 (profiles/r02d_smooth_branch.log), us per iteration at
+        # 4096 rays x 128 samples / 2048 x 43: in line 449 / 213; fork 1 426 / 203; fork 2 433 / 187; fork 2 + stagger 2
+        # 424 / 186; a branch that starts together with decode_bwd_q (stagger 8) costs more than it hides (453 / 207).
+        self.smooth_fork = int(os.environ.get('NRT_SMOOTH_FORK', '2'))
+        self.smooth_stagger = int(os.environ.get('NRT_SMOOTH_STAGGER', '2'))
         self._branch = None
         self.launches_per_iter = {False: 0, True: 0}
 
@@ -293,6 +294,8 @@ class MappingStep:
         else:
             self._branch.wait_event(after)
         with torch.cuda.stream(self._branch):
+            for _ in range(self.smooth_stagger):
+                self.smooth_loss.zero_()
             p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
                              self.smooth_loss, self.G.grid, self.ws_smooth, part=self.rank, n_parts=self.world)
         return 2
