@@ -237,7 +237,8 @@ def side_config(name, cfg, bound, B_local, dev, pg, world, rank, scaling, steps=
                         lin(3, 32), torch.full(plan.uncert_dims, 3.0))
     ms = MappingStep(plan, cfg, B_local, dev, init=init, process_group=pg)
     del init
-    frame = SyntheticFrame(bound, seed=300 + rank)
+    frame = SyntheticFrame(bound, seed=300)            # one frame, every rank its own pixel draws (shards of one global batch)
+    frame.gen.manual_seed(3000 + rank)
     batches = [frame.sample_packed(B_local).to(dev) for _ in range(4)]
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     evs = []
@@ -464,7 +465,11 @@ def run_ours(args):
     init = FieldTensors((torch.rand(plan.n_grid_floats, generator=g) * 2 - 1) * 1e-4, lin(32, 80), lin(16, 32), lin(32, 63),
                         lin(3, 32), torch.full(plan.uncert_dims, 3.0))
     ms = MappingStep(plan, cfg, B, dev, init=init, process_group=pg, use_graph=not args.no_graph)
-    frame = SyntheticFrame(OFFICE0_BOUND, seed=100 + rank)
+    # data parallel = one global batch of world x B rays split evenly: every rank draws its own pixels of the SAME synthetic frame
+    # (statistically identical shards, like shards of a batch sampled from one key-frame database; a different camera pose per
+    # rank would add a 5-8 % spread of the forward time between ranks that a sharded batch does not have)
+    frame = SyntheticFrame(OFFICE0_BOUND, seed=100)
+    frame.gen.manual_seed(1000 + rank)
     host_batches = [frame.sample_packed(B, pin=True) for _ in range(W + K)]
     dev_batches = [hb.to(dev) for hb in host_batches]
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # 256 MB > 126 MB L2
@@ -635,7 +640,9 @@ def run_ours(args):
         'config': {'workload': f'Replica office_0 shape, 680x1200 synthetic frame, mapping iteration (render fwd + losses + bwd + '
                                f'smoothness + Adam), {B} rays/GPU x {S} samples/ray (n_samples_d={N_SAMPLES_D}+n_range_d=11), '
                                f'hash_size 16, random-init weights',
-                   'rays_per_step_per_gpu': B, 'samples_per_ray': S, 'parallelism': f'ray-sharded dp{world}, grad all-reduce',
+                   'rays_per_step_per_gpu': B, 'samples_per_ray': S, 'parallelism': f'ray-sharded dp{world} (shards = per-rank pixel draws of one frame), '
+                                  + ('exchanges over NVLink peer memory inside our kernels' if ms.peers is not None else
+                                     'NCCL all-reduces' if world > 1 else 'single shard'),
                    'l2': 'explicit 256 MB L2 flush before every timed step', 'cuda_graph': not args.no_graph},
         'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': 10 * B * 4, 'd2h_bytes_per_step': 8 * 4,
                 'ms_per_step': 1e3 * t_e2e / K},

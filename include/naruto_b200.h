@@ -260,7 +260,7 @@ int nrt_step_begin(int32_t* counter_dev, int32_t delta, uint64_t seed, float* ra
  * torch.distributed._symmetric_memory).  All pointer tables are HOST arrays of DEVICE pointers indexed by rank.
  *   bucket[r]     dev fp32 [pad4(total) + 4]  flat gradient [grid | w1 | w2 | w3 | w4 | uncert], the smoothness-loss slot behind it
  *   theta[r]      dev fp32 [pad4(total)]      flat parameters, same layout
- *   stats_pad[r]  dev fp64 [world * NRT_N_STATS]
+ *   stats_pad[r]  dev u64  [world * 2 * NRT_N_STATS], zero-filled once (flag-carrying words: 32 data bits + exchange number)
  *   flags[r]      dev u32  [3 * 8], zero-filled once
  * Every rank must make the same sequence of calls (one nrt_stats_exchange, then one nrt_adam_step_peers per iteration). */
 typedef struct NrtPeerTable {
@@ -269,6 +269,8 @@ typedef struct NrtPeerTable {
   float* theta[8];
   double* stats_pad[8];
   uint32_t* flags[8];
+  float* bucket_mc;           /* optional: NVSwitch multicast (NVLS) address of the same bucket region on all ranks, or NULL; with it */
+  float* theta_mc;            /* the gradient sum is one in-switch multimem.ld_reduce and the parameter all-gather one multimem.st */
 } NrtPeerTable;
 
 /* One Adam parameter group of the flat vector: floats [begin, end), begin a multiple of 4 and every buffer padded to a whole
@@ -280,6 +282,8 @@ typedef struct NrtAdamGroup {
   float lr, beta1, beta2, eps, weight_decay;
   const int32_t* step_dev;
   int32_t enabled;
+  int32_t keep_grad;   /* nrt_adam_step_peers only: 1 = do not clear the gradients that were read on the peers (the owner of each
+                        * bucket clears its own copy before the next accumulation: no zero-stores over NVLink) */
 } NrtAdamGroup;
 
 /* all-reduce of the loss statistics + nrt_loss_finalize in one launch: stats (dev, this rank's sums from
@@ -349,8 +353,12 @@ int nrt_active_select(const float* rays_o, const float* rays_d, const float* tar
 /* Profiling aid: with NRT_BWD_DEBUG=8 in the environment the backward kernel stamps clock64() at its phase boundaries
  * (per CTA: entry, prologue done, MLP loop done, scatter loop done, before flush, after flush, end); this copies the
  * [256][8] int64 table to host memory (synchronises).  A NEGATIVE `bytes` reads |bytes| of the forward kernel's table instead
- * (NRT_FWD_DEBUG=1: per CTA the cycles of sub-CTA 0 in prologue / ray staging / tiles / compositing / total / incl. statistics tail). */
+ * (NRT_FWD_DEBUG=1: per CTA the cycles of sub-CTA 0 in prologue / ray staging / tiles / compositing / total / incl. statistics tail).
+ * With bit 30 set in `bytes` (and NRT_PEER_DEBUG=1): the globaltimer stamps of nrt_adam_step_peers' phases (8 x u64). */
 int nrt_debug_read(void* host_dst, int32_t bytes);
+/* Profiling aid: a one-thread launch that writes the GPU's nanosecond %globaltimer to dst (dev u64) -- stage boundaries of a
+ * captured iteration (MappingStep.trace_graph), which events cannot time inside a CUDA graph. */
+int nrt_debug_stamp(uint64_t* dst_dev, void* stream);
 int nrt_selftest_umma(int mode, const float* a, const float* b, int32_t k, int32_t n, int passes, float* d, void* stream);
 /* Raw probe: a_img / b_img (dev) are copied verbatim into shared memory and multiplied as d[128,n] with the given
  * descriptor fields (bytes): leading / stride byte offsets, per-k-step start-address advance, MN-major flags. */

@@ -44,12 +44,12 @@ class NrtRenderOut(C.Structure):
 
 class NrtPeerTable(C.Structure):
     _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('bucket', C.c_void_p * 8), ('theta', C.c_void_p * 8),
-                ('stats_pad', C.c_void_p * 8), ('flags', C.c_void_p * 8)]
+                ('stats_pad', C.c_void_p * 8), ('flags', C.c_void_p * 8), ('bucket_mc', C.c_void_p), ('theta_mc', C.c_void_p)]
 
 
 class NrtAdamGroup(C.Structure):
     _fields_ = [('begin', C.c_int64), ('end', C.c_int64), ('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float),
-                ('eps', C.c_float), ('weight_decay', C.c_float), ('step_dev', C.c_void_p), ('enabled', C.c_int32)]
+                ('eps', C.c_float), ('weight_decay', C.c_float), ('step_dev', C.c_void_p), ('enabled', C.c_int32), ('keep_grad', C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/naruto_b200.h declares
@@ -84,6 +84,7 @@ SIGNATURES = {
     'nrt_erp_depth2dist': (C.c_int, [c_fp, C.c_int32, C.c_int32, c_fp, c_fp, c_fp, C.c_int32, c_fp, _P]),
     'nrt_erp_depth2dist_analytic': (C.c_int, [c_fp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.c_float, c_fp, _P]),
     'nrt_debug_read': (C.c_int, [C.c_void_p, C.c_int32]),
+    'nrt_debug_stamp': (C.c_int, [c_fp, _P]),
     'nrt_stats_exchange': (C.c_int, [C.POINTER(NrtPeerTable), c_fp, c_fp, c_fp, _P]),
     'nrt_adam_step_groups': (C.c_int, [c_fp, c_fp, c_fp, c_fp, C.POINTER(NrtAdamGroup), C.c_int32, C.c_int, _P]),
     'nrt_adam_step_peers': (C.c_int, [C.POINTER(NrtPeerTable), c_fp, c_fp, C.POINTER(NrtAdamGroup), C.c_int32, C.c_int64, c_fp, c_fp, c_fp,

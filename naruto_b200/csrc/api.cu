@@ -31,6 +31,7 @@ int launch_encode_bwd(const NrtPlan*, const float*, const PointSource&, int64_t,
                       cudaStream_t);
 int q_trace_read(void*, int);
 int ws_trace_read(void*, int);
+int peer_trace_read(void*, int);
 int launch_smooth(const NrtPlan*, const float*, const float*, int, double, double, float, float*, float*, void*, int, int, cudaStream_t);
 int launch_adam(float*, float*, float*, float*, int64_t, int, const int*, float, float, float, float, float, int, int,
                 cudaStream_t);
@@ -505,8 +506,22 @@ int nrt_active_select(const float* rays_o, const float* rays_d, const float* tar
 
 int nrt_debug_read(void* host_dst, int32_t bytes) {
   NRT_REQUIRE(host_dst && bytes != 0, "debug_read arguments");
+  if (bytes > 0 && (bytes & (1 << 30))) return peer_trace_read(host_dst, bytes & ~(1 << 30));      // NRT_PEER_DEBUG=1 table
   if (bytes < 0) return ws_trace_read(host_dst, -bytes);     // negative size: the forward kernel's table (NRT_FWD_DEBUG=1)
   return q_trace_read(host_dst, bytes);
+}
+
+__global__ void stamp_kernel(unsigned long long* dst) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *dst = t;
+}
+
+int nrt_debug_stamp(uint64_t* dst_dev, void* stream) {
+  NRT_REQUIRE(dst_dev, "debug_stamp arguments");
+  stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(dst_dev));
+  NRT_CUDA_CHECK(cudaGetLastError());
+  return NRT_OK;
 }
 
 int nrt_selftest_umma(int mode, const float* a, const float* b, int32_t k, int32_t n, int passes, float* d, void* stream) {

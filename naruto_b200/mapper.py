@@ -126,6 +126,10 @@ class FusedState:
         sharded moments, all-gather them first (gather=False skips that)."""
         if gather:
             self.gather_moments()
+        if self.peers is not None:
+            # the peer-memory iteration clears a rank's [grid | decoder] gradients at the START of the next iteration (no
+            # zero-stores over NVLink): leave them as optimizer.zero_grad() would for whoever runs next
+            self.grad[:self.n_grid + self.n_dec].zero_()
         if self._bound is None:
             return
         model, map_opt, unc_opt = self._bound
@@ -225,6 +229,12 @@ class MappingStep:
         self.smooth_fork = int(os.environ.get('NRT_SMOOTH_FORK', '2'))
         self.smooth_stagger = int(os.environ.get('NRT_SMOOTH_STAGGER', '2'))
         self._branch = None
+        self._zero_branch = None
+        self.local_zero = os.environ.get('NRT_DP_LOCAL_ZERO', '1') == '1'
+        # profiling aid (tools/probe_dp.py): NRT_STEP_STAMPS=1 puts a one-thread globaltimer stamp after every stage of the
+        # iteration, also inside the captured graph, where events cannot time; stamps[k] <-> stamp_names[k]
+        self.stamps = torch.zeros(16, dtype=torch.int64, device=self.dev) if os.environ.get('NRT_STEP_STAMPS') == '1' else None
+        self.stamp_names, self._stamp_i = [], 0
         self.launches_per_iter = {False: 0, True: 0}
 
     # -------------------------------------------------------------------------------------------
@@ -233,7 +243,9 @@ class MappingStep:
         p, n = self.plan, 0
         smooth = self.smooth_on if smooth is None else (bool(smooth) and self.smooth_w > 0)
         fused_losses = self.losses if self.world == 1 else None      # one shard: the render kernel's last CTA finalizes the losses
-        forked = False
+        forked = zeroing = False
+        self._stamp_i = 0
+        self._mark('start')
         if self.external_random:                            # test hook: caller-written self.u / self.rand6 (the reference's draws)
             p.counter_add(self.map_step, 1); n += 1
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=self.u,
@@ -243,28 +255,43 @@ class MappingStep:
             # keyed by (seed, step counter): nothing host-side changes between graph replays
             p.iteration_begin(self.map_step, self.unc_step if with_uncert_step else None, self.base_seed,
                               self.rand6 if smooth else None); n += 1
-            if smooth and self.smooth_fork == 1:
+            if self.peers is not None and self.local_zero:
+                # every rank clears its own [grid | decoder] gradients, on a branch beside the forward (the peers read them in the
+                # previous iteration's optimiser launch, which ended with a barrier): no zero-stores over NVLink
+                if self._zero_branch is None:
+                    self._zero_branch = torch.cuda.Stream(device=self.dev)
+                self._zero_branch.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._zero_branch):
+                    self.grad[:self.n_grid + self.n_dec].zero_()
+                zeroing = True
+            if smooth and self.smooth_fork == 1 and not zeroing:
                 n += self._smooth_branch(); forked = True
             ev = torch.cuda.current_stream().record_event() if smooth and self.smooth_fork == 3 else None
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=None,
                                seed=self.seed, seed_step=self.map_step, losses=fused_losses); n += 1
             if ev is not None:                              # forked before the forward, launched after it
                 n += self._smooth_branch(ev); forked = True
+        if zeroing:
+            torch.cuda.current_stream().wait_stream(self._zero_branch)
+        self._mark('forward')
         if fused_losses is None:                            # N > 1: the losses are ratios of GLOBAL sums
             if self.peers is not None:                      # exchange + finalize in one launch over peer memory
                 self.peers.stats_exchange(self.stats, self.losses); n += 1
             else:
                 reduce_stats(self.stats, self.pg)
                 p.loss_finalize(self.stats, self.losses); n += 1
+        self._mark('stats_exchange')
         if smooth and self.smooth_fork == 2:
             n += self._smooth_branch(); forked = True
         p.render_bwd(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, self.loss_grad,
                      self.G, workspace=self.ws_bwd); n += 3     # composite_bwd, decode_bwd_q, wgrad_reduce
+        self._mark('backward')
         if smooth and not forked:                           # ray-independent term: every rank takes one slab of the lattice
             p.smooth_fwd_bwd(self.P.grid, self.rand6, self.smooth_n, self.smooth_vox, self.smooth_margin, self.smooth_w,
                              self.smooth_loss, self.G.grid, self.ws_smooth, part=self.rank, n_parts=self.world); n += 2
         elif forked:
             torch.cuda.current_stream().wait_stream(self._branch)      # join: the optimiser needs both gradients
+        self._mark('smooth/join')
         ng, nd = self.n_grid, self.n_dec
         if with_uncert_step and self.external_random:       # (otherwise iteration_begin advanced the uncertainty step counter)
             p.counter_add(self.unc_step, 1); n += 1
@@ -276,11 +303,23 @@ class MappingStep:
                   (ng + nd, ng + nd + self.n_unc, 1.0, 0.9, 0.999, 1e-8, 0.0, self.unc_step, bool(with_uncert_step))]
         if self.peers is not None:
             # reduce-scatter + Adam (all three groups) + all-gather in ONE launch over peer memory (csrc/peer.cu)
-            self.peers.adam_step(self.exp_avg, self.exp_avg_sq, groups, self.smooth_total if smooth else None); n += 1
+            self.peers.adam_step(self.exp_avg, self.exp_avg_sq, groups, self.smooth_total if smooth else None,
+                                 keep_grad=[zeroing, zeroing, False]); n += 1
+            self._mark('adam')
             return n
         reduce_grads(self.bucket, self.pg)
         p.adam_step_groups(self.theta, self.grad, self.exp_avg, self.exp_avg_sq, groups, zero_grad=True); n += 1
+        self._mark('adam')
         return n
+
+    def _mark(self, name):
+        if self.stamps is None:
+            return
+        k = self._stamp_i
+        self._stamp_i += 1
+        if k >= len(self.stamp_names):
+            self.stamp_names.append(name)
+        L.check(self.plan.lib.nrt_debug_stamp(self.stamps.data_ptr() + 8 * k, torch.cuda.current_stream().cuda_stream))
 
     def _smooth_branch(self, after=None):
         """Launch the smoothness term on a second stream forked off the current one (inside a capture this becomes a parallel

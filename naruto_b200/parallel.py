@@ -7,6 +7,8 @@ Two exchanges per iteration, both plain all-reduces issued on the compute stream
   2. the flat fp32 gradient bucket [grid | w1 | w2 | w3 | w4 | uncert] before the (replicated) Adam step.
 These helpers are backend-agnostic (NCCL on the GPUs, gloo in the CPU tests).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -59,7 +61,7 @@ class PeerExchange:
         # gradients [0, total), then (behind the last float4 of the gradients) the smoothness-loss slot
         self.smooth_slot = pad4(total)
         off_stats = off_bucket + pad4(total) + 4               # floats; fp64 region must be 8-byte aligned (it is: multiples of 4)
-        off_flags = off_stats + 2 * self.world * n_stats
+        off_flags = off_stats + 2 * self.world * 2 * n_stats      # u64 [world][2 * n_stats]: flag-carrying words (csrc/peer.cu)
         n_floats = off_flags + 32
         name = group.group_name
         import warnings
@@ -83,6 +85,13 @@ class PeerExchange:
             t.bucket[r] = base + 4 * off_bucket
             t.stats_pad[r] = base + 4 * off_stats
             t.flags[r] = base + 4 * off_flags
+        # NVSwitch multicast mapping of the same allocation (NVLS), when the system provides one: in-switch gradient reduction.
+        # Opt-in (NRT_DP_MULTICAST=1): measured on 8 B200s it shortens the optimiser launch's slice phase (25.4 -> 21.1 us) but the
+        # iteration as a whole came out slower (477 vs 467 us, profiles/r02d_dp_stages.log); at 2 ranks it doubles the traffic.
+        mc = int(getattr(self.handle, 'multicast_ptr', 0) or 0)
+        self.multicast = bool(mc) and os.environ.get('NRT_DP_MULTICAST', '0') == '1'
+        if self.multicast:
+            t.bucket_mc, t.theta_mc = mc + 4 * off_bucket, mc + 4 * off_theta
         self.table = t
         self.xchg = torch.zeros(1, dtype=torch.int32, device=device)       # exchange counter (never restored by graph warm-ups)
         self.done = torch.zeros(1, dtype=torch.int32, device=device)
@@ -95,13 +104,14 @@ class PeerExchange:
         L.check(self.lib.nrt_stats_exchange(C.byref(self.table), L.ptr(stats), L.ptr(self.xchg), L.ptr(losses),
                                             torch.cuda.current_stream().cuda_stream))
 
-    def adam_step(self, exp_avg, exp_avg_sq, groups, smooth_total):
-        """groups: list of (begin, end, lr, beta1, beta2, eps, weight_decay, step_dev tensor, enabled)."""
+    def adam_step(self, exp_avg, exp_avg_sq, groups, smooth_total, keep_grad=None):
+        """groups: list of (begin, end, lr, beta1, beta2, eps, weight_decay, step_dev tensor, enabled); keep_grad: per group, True =
+        the gradients are not cleared on the peers (every rank clears its own bucket before it accumulates again)."""
         C, L = self._C, self._L
         arr = (L.NrtAdamGroup * len(groups))()
-        for a, (b, e, lr, b1, b2, eps, wd, step_dev, en) in zip(arr, groups):
+        for a, (b, e, lr, b1, b2, eps, wd, step_dev, en), keep in zip(arr, groups, keep_grad or [False] * len(groups)):
             a.begin, a.end, a.lr, a.beta1, a.beta2, a.eps, a.weight_decay = b, e, lr, b1, b2, eps, wd
-            a.step_dev, a.enabled = L.ptr(step_dev), int(en)
+            a.step_dev, a.enabled, a.keep_grad = L.ptr(step_dev), int(en), int(keep)
         L.check(self.lib.nrt_adam_step_peers(C.byref(self.table), L.ptr(exp_avg), L.ptr(exp_avg_sq), arr, len(groups), self.smooth_slot,
                                              L.ptr(smooth_total) if smooth_total is not None else None, L.ptr(self.xchg),
                                              L.ptr(self.done), torch.cuda.current_stream().cuda_stream))

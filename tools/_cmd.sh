@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-NRT_PROFILE_MAPPER=1 python bench.py --steps 5 --warmup 3 --no-side-configs --no-torch-gpu-baseline --no-cpu-baseline --sweep-rays 0 > gpurun_out/r3g_bench.json 2> gpurun_out/r3g_prof.txt
-python -c "
-import json
-d=json.loads(open('gpurun_out/r3g_bench.json').read().strip().splitlines()[-1]); print(d.get('e2e_mapper'))"
-python -m pytest tests/test_coslam_mapper.py -x -q 2>&1 | tail -2
+for mc in 1 0; do
+NRT_DP_MULTICAST=$mc timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 tools/probe_dp.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$\|NCCL"
+done > gpurun_out/r3p_dp_stages_8gpu.log
+cat gpurun_out/r3p_dp_stages_8gpu.log
