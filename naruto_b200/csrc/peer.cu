@@ -178,7 +178,10 @@ __device__ __forceinline__ void adam_peers_range(const PeerTable& T, float* __re
   const int64_t n4 = G.end4 - G.begin4;
   const int64_t lo = G.begin4 + n4 * R / W, hi = G.begin4 + n4 * (R + 1) / W;
   const bool clear = !G.keep_grad;
-  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + t; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+  // warp-major over the grid (warp w of CTA b is global warp w * gridDim + b): a slice shorter than the grid still spreads
+  // evenly over every SM instead of filling the first CTAs only
+  const int64_t gw = (int64_t)(t >> 5) * gridDim.x + blockIdx.x;
+  for (int64_t i = lo + gw * 32 + (t & 31); i < hi; i += (int64_t)gridDim.x * blockDim.x) {
     // every load of the element is issued before the first use: ONE trip over NVLink per element, not one per peer
     float4 th = reinterpret_cast<const float4*>(T.theta[R])[i];
     float4 m = reinterpret_cast<float4*>(exp_avg)[i], v = reinterpret_cast<float4*>(exp_avg_sq)[i];
