@@ -203,6 +203,7 @@ class MappingStep:
         self.rand6 = torch.zeros(6, **f32)
         self.stats = plan.new_stats(self.dev)
         self.losses = torch.zeros(L.N_LOSS, **f32)
+        self.host_in = self.host_losses = None       # pinned host buffers of step_host(), allocated on first use
         self.smooth_loss = self.bucket[st.smooth_slot:st.smooth_slot + 1]
         # N > 1 with peer memory: the sum of the ranks' slab losses lands here (the bucket slot itself is rank-local then)
         self.smooth_total = torch.zeros(1, **f32)
@@ -339,9 +340,9 @@ class MappingStep:
                              self.smooth_loss, self.G.grid, self.ws_smooth, part=self.rank, n_parts=self.world)
         return 2
 
-    def _graph(self, with_uncert_step, smooth=None):
+    def _graph(self, with_uncert_step, smooth=None, host_io=False):
         smooth = self.smooth_on if smooth is None else (bool(smooth) and self.smooth_w > 0)
-        key = (bool(with_uncert_step), smooth)
+        key = (bool(with_uncert_step), smooth, bool(host_io))
         if key not in self._graphs:
             # warm-up outside capture (lazy attribute/module init inside the library and torch RNG)
             side = torch.cuda.Stream(device=self.dev)
@@ -353,9 +354,12 @@ class MappingStep:
             for b, s in zip(self.state.persistent(), saved):
                 b.copy_(s)
             g = torch.cuda.CUDAGraph()
-            cap = torch.cuda.Stream(device=self.dev, priority=-1) if os.environ.get('NRT_MAIN_PRIO') == '1' else None
-            with torch.cuda.graph(g, stream=cap):
+            with torch.cuda.graph(g):
+                if host_io:          # the iteration's rays from the pinned input buffer ... (memcpy nodes of the same graph)
+                    self.inbuf.copy_(self.host_in, non_blocking=True)
                 self.launches_per_iter[bool(with_uncert_step)] = self._body(with_uncert_step, smooth)
+                if host_io:          # ... and its losses back into pinned host memory
+                    self.host_losses.copy_(self.losses, non_blocking=True)
             for b, s in zip(self.state.persistent(), saved):
                 b.copy_(s)
             self._graphs[key] = g
@@ -377,6 +381,28 @@ class MappingStep:
     def load_packed(self, buf):
         """One packed [10*B] host (pinned) or device buffer, see SyntheticFrame.sample_packed."""
         self.inbuf.copy_(buf, non_blocking=True)
+
+    def step_host(self, packed=None, with_uncert_step=None, smooth=None):
+        """One mapping iteration fed from HOST memory and read back to it, as ONE graph launch: H2D of the packed ray batch
+        (`self.host_in`, pinned [10*B] = [o | d | rgb | depth]; a `packed` host tensor is first copied into it), the iteration,
+        D2H of the losses into `self.host_losses` (pinned [8]; valid once the stream -- or an event recorded after this call --
+        has been synchronised).  Against load_packed() + step() + losses.cpu() this saves two API round trips per iteration."""
+        if self.host_in is None:
+            self.host_in = torch.empty(10 * self.B, dtype=torch.float32, pin_memory=True)
+            self.host_losses = torch.zeros(L.N_LOSS, dtype=torch.float32, pin_memory=True)
+        if packed is not None and packed.data_ptr() != self.host_in.data_ptr():
+            self.host_in.copy_(packed.reshape(-1))
+        with_unc = (self.it + 1) % 5 == 0 if with_uncert_step is None else bool(with_uncert_step)
+        if self.use_graph:
+            self._graph(with_unc, smooth, host_io=True).replay()
+        else:
+            self.inbuf.copy_(self.host_in, non_blocking=True)
+            self.launches_per_iter[with_unc] = self._body(with_unc, smooth)
+            self.host_losses.copy_(self.losses, non_blocking=True)
+        self.it += 1
+        self.state.n_map_steps += 1
+        self.state.n_unc_steps += 1 if with_unc else 0
+        return self.host_losses
 
     def step(self, rays_o=None, rays_d=None, target_rgb=None, target_d=None, with_uncert_step=None, smooth=None):
         """One mapping iteration.  Returns the device tensor of the five losses (no host sync).

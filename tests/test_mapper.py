@@ -202,3 +202,34 @@ def test_grouped_adam_equals_per_group_adam_and_skips_disabled_groups():
             assert ga_acc[sizes[0] + sizes[1]:].abs().max() > 0 and (ga_acc[:sizes[0] + sizes[1]] == 0).all()
         else:
             assert (ga_acc == 0).all()
+
+
+def test_step_host_is_the_same_iteration_fed_from_pinned_memory():
+    """step_host (H2D memcpy node + iteration + D2H memcpy node in one graph) against load_packed + step + losses.cpu() on a
+    twin: the first iteration's losses are bit-identical (same parameters, rays and jitter), later ones agree to the tolerance
+    of the unordered table reductions."""
+    dev = torch.device('cuda:0')
+    from naruto_b200.configs import replica_office0, OFFICE0_BOUND
+    from naruto_b200.field import FieldPlan, FieldTensors
+    from naruto_b200.mapper import MappingStep
+    from naruto_b200.synthetic import SyntheticFrame
+    cfg = replica_office0()
+    plan = FieldPlan(cfg, OFFICE0_BOUND)
+    g = torch.Generator().manual_seed(2)
+    lin = lambda o, i: (torch.rand(o, i, generator=g) * 2 - 1) / (i ** 0.5)
+    init = FieldTensors((torch.rand(plan.n_grid_floats, generator=g) * 2 - 1) * 1e-2, lin(32, 80), lin(16, 32), lin(32, 63), lin(3, 32),
+                        torch.full(plan.uncert_dims, 3.0))
+    B = 300
+    a = MappingStep(plan, cfg, B, dev, init=init)
+    b = MappingStep(plan, cfg, B, dev, init=init)
+    frame = SyntheticFrame(OFFICE0_BOUND, seed=4)
+    for it in range(6):
+        host = frame.sample_packed(B, pin=True)
+        a.load_packed(host)
+        la = a.step().cpu()
+        lb = b.step_host(host)
+        torch.cuda.synchronize()
+        if it == 0:
+            assert torch.equal(la, lb), (la, lb)
+        assert torch.allclose(la[:5], lb[:5], rtol=2e-3, atol=1e-7), (it, la, lb)
+    assert int(a.state.map_step.item()) == int(b.state.map_step.item()) == 6 and int(b.state.unc_step.item()) == 1
