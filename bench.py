@@ -547,7 +547,7 @@ def run_ours(args):
         kern = {k: {'ms': round(v[0], 4), 'algorithmic_GB_per_s': round(v[1] / v[0] / 1e6, 1)} for k, v in kt.items()}
         top = max(kt, key=lambda k: kt[k][0])
         ach = kt[top][1] / kt[top][0] / 1e6
-        traffic, lsu = None, None
+        traffic, lsu, tjd = None, None, {}
         tj = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tj):
             # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (same workload)
@@ -567,7 +567,12 @@ def run_ours(args):
                     'red_lane_floor_ms': round(lsu['red_lanes_per_launch'] * lsu['red_ns_per_lane_per_sm'] * 1e-6 / 148, 4),
                     'red_lanes_per_launch': lsu['red_lanes_per_launch'], 'shared_wavefronts_per_launch': lsu['shared_wavefronts_per_launch']},
                 'hash_gather': {'kernel': 'render_fwd_ws_kernel', 'achieved': kern['render_fwd_ws_kernel']['algorithmic_GB_per_s'],
-                                'frac': round(kern['render_fwd_ws_kernel']['algorithmic_GB_per_s'] / hbm, 4)}}
+                                'frac': round(kern['render_fwd_ws_kernel']['algorithmic_GB_per_s'] / hbm, 4),
+                                # what bounds the gather is the rate at which an SM's load pipe serves divergent 8-byte reads:
+                                # corner reads per second against the measured rate of independent random reads from an
+                                # L2-resident table (tools/micro/random_gather.cu; x-neighbour pairs share a wavefront, so > 1 is possible)
+                                'corner_reads_G_per_s': round(B * S * 128 / kt['render_fwd_ws_kernel'][0] / 1e6, 1),
+                                'random_read_ceiling_G_per_s': tjd.get('random_gather_microbench', {}).get('l2_resident_0p5MB_G_reads_per_s')}}
     sweep = None
     if rank == 0 and world == 1 and args.sweep_rays > 0:
         # BASELINE.json configs[4]: uncertainty-only forward sweep, 1M rays x 128 samples, no backward, only the per-ray
