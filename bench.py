@@ -417,11 +417,13 @@ def mapper_path(dev, torch, n_calls=6, n_keyframes=24):
     fm = cm._mapper(s)
     rays = max(fm.steps) if fm.steps else cfg['mapping']['sample']       # mapping.sample + the current-frame tail
     fm.release()
-    return {'what': 'coslam_mapper.global_BA on HOST frames: H2D of the 680x1200 frame + device-side sampling + '
+    return {'what': 'coslam_mapper.global_BA on HOST frames: H2D of the 680x1200 colour + depth images + device-side sampling + '
                     f'{iters} fused mapping iterations + D2H of the loss, per call (wall clock, synchronised)',
             'ms_per_call': round(1e3 * tsec, 3), 'iterations_per_call': iters, 'rays_per_iteration': rays,
             'key_frames': n_keyframes, 'value': rays * iters / tsec, 'unit': UNIT, 'finite': bool(loss == loss),
-            'h2d_bytes_per_call': H * W * 7 * 4, 'd2h_bytes_per_call': 4}
+            'h2d_bytes_per_call': H * W * 4 * 4, 'd2h_bytes_per_call': 4,
+            'note': 'rgb + depth go up with every call; the camera-ray image (the same host tensor for every frame of a run) is '
+                    'uploaded once (ray_sampler.device_directions)'}
 
 
 def run_ours(args):

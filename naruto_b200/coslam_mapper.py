@@ -24,7 +24,8 @@ import torch
 from . import _lib as L
 from .field import FieldTensors
 from .mapper import FusedState, MappingStep
-from .ray_sampler import (DeviceActiveRaySampler, DeviceKeyFrameDatabase, pack_frame, sample_indices, sample_mapping_batch)
+from .ray_sampler import (DeviceActiveRaySampler, DeviceKeyFrameDatabase, device_directions, pack_frame, sample_indices,
+                          sample_mapping_batch)
 
 
 class FusedMapper:
@@ -115,7 +116,7 @@ def first_frame_mapping(slam, batch, n_iters=100, indices=None):
     slam.est_c2w_data_rel[0] = c2w
     slam.model.train()
     H, W, n = slam.dataset.H, slam.dataset.W, int(cfg['mapping']['sample'])
-    frame = pack_frame(batch['direction'].squeeze(0).to(dev), batch['rgb'].squeeze(0).to(dev), batch['depth'].squeeze(0).to(dev))
+    frame = pack_frame(device_directions(batch['direction'], dev).squeeze(0), batch['rgb'].squeeze(0).to(dev), batch['depth'].squeeze(0).to(dev))
     poses = c2w.reshape(1, 4, 4).float().contiguous()
     ms = fm.step_for(n, n_iters)
     if cfg['decoder']['uncert_grid']:
@@ -161,7 +162,7 @@ def global_BA(slam, batch, cur_frame_id, draws=None):
     poses_all = torch.stack([slam.est_c2w_data[i] for i in range(0, cur_frame_id, kf_every)] + [slam.est_c2w_data[cur_frame_id]])
     poses_all = poses_all.to(dev, torch.float32).contiguous()
     slam.model.train()
-    current_rays = pack_frame(batch['direction'].squeeze(0).to(dev), batch['rgb'].squeeze(0).to(dev), batch['depth'].squeeze(0).to(dev))
+    current_rays = pack_frame(device_directions(batch['direction'], dev).squeeze(0), batch['rgb'].squeeze(0).to(dev), batch['depth'].squeeze(0).to(dev))
     sampler = getattr(slam, 'active_ray_sampler', None) if cfg['mapping']['active_ray'] else None
     if sampler is not None and not isinstance(sampler, DeviceActiveRaySampler):
         raise L.NrtError('the fused global_BA needs naruto_b200.ray_sampler.DeviceActiveRaySampler as self.active_ray_sampler')

@@ -38,6 +38,29 @@ def camera_rays(H, W, fx, fy, cx, cy, device):
     return out
 
 
+_DIRECTION_CACHE = {}
+
+
+def device_directions(direction, dev):
+    """The camera-ray image of a batch on the device.  The reference hands the SAME host tensor over with every frame
+    (`batch['direction'] = self.rays_d.unsqueeze(0)`, src/slam/coslam/coslam.py:565; datasets/dataset.py:122): it is uploaded once
+    and reused while the host tensor's storage, shape, version counter and a 64-element content fingerprint stay the same
+    (9.8 MB of the 22.8 MB a 680x1200 frame would otherwise send up per global_BA call and again per key frame)."""
+    if direction.device.type != 'cpu':
+        return direction.to(dev)
+    flat = direction.reshape(-1)
+    probe = flat[:: max(1, flat.numel() // 64)][:64].clone()
+    key = (str(dev), direction.data_ptr(), tuple(direction.shape), direction._version, direction.dtype)
+    hit = _DIRECTION_CACHE.get(key)
+    if hit is not None and torch.equal(hit[0], probe):
+        return hit[1]
+    if len(_DIRECTION_CACHE) >= 4:
+        _DIRECTION_CACHE.clear()
+    on_dev = direction.to(dev)
+    _DIRECTION_CACHE[key] = (probe, on_dev)
+    return on_dev
+
+
 def pack_frame(direction, rgb, depth):
     """[H*W, 7] = (direction 3, rgb 3, depth 1) from the three images of a batch (device tensors)."""
     lib = L.load()
@@ -100,7 +123,7 @@ class DeviceKeyFrameDatabase:
     def add_keyframe(self, batch, filter_depth=False, idxs=None):
         """src/slam/coslam/model/keyframe.py:38-60.  batch: direction [1,H,W,3], rgb [1,H,W,3], depth [1,H,W], frame_id."""
         dev = self.device
-        frame = pack_frame(batch['direction'].to(dev), batch['rgb'].to(dev), batch['depth'].to(dev))
+        frame = pack_frame(device_directions(batch['direction'], dev), batch['rgb'].to(dev), batch['depth'].to(dev))
         P = self.num_rays_to_save
         cnt = None
         if idxs is None:

@@ -142,3 +142,20 @@ def test_keyframe_with_no_valid_depth_leaves_its_slot_untouched():
     assert len(db) == 2 and db.frame_ids.tolist() == [0, 5]
     assert db.rays[0].abs().sum() > 0 and (db.rays[0, :, 6] > 0).all()
     assert db.rays[1].abs().sum() == 0, 'no pixel of an all-invalid frame is stored'
+
+
+def test_direction_image_is_uploaded_once_and_re_uploaded_when_it_changes():
+    """batch['direction'] is the same host tensor for every frame of a run (src/slam/coslam/coslam.py:565): the device copy is
+    reused while storage, version and a content fingerprint match, and refreshed as soon as the host tensor is written to."""
+    from naruto_b200.ray_sampler import device_directions
+    from naruto_b200.synthetic import camera_rays
+    host = camera_rays(60, 80).unsqueeze(0)
+    a = device_directions(host, 'cuda')
+    b = device_directions(host.unsqueeze(0).squeeze(0), 'cuda')          # another view object of the same storage
+    assert a.data_ptr() == b.data_ptr() and torch.equal(a.cpu(), host)
+    host.mul_(2.0)                                                        # in-place write: version counter and content change
+    c = device_directions(host, 'cuda')
+    assert torch.equal(c.cpu(), host) and not torch.equal(c, a)
+    other = host.clone()
+    d = device_directions(other, 'cuda')
+    assert d.data_ptr() != c.data_ptr() and torch.equal(d.cpu(), other)

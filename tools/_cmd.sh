@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_mapper.py -q -m gpu -k "grouped or step_host or random_draws or slabs" > gpurun_out/r02e_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -3 gpurun_out/r02e_memcheck.log
-timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/probe_bwd.py 7 32 > gpurun_out/r02e_racecheck_backward.log 2>&1; echo "racecheck bwd rc=$?"; tail -2 gpurun_out/r02e_racecheck_backward.log
-timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python tools/probe_fwd.py 7 32 > gpurun_out/r02e_racecheck_forward.log 2>&1; echo "racecheck fwd rc=$?"; tail -2 gpurun_out/r02e_racecheck_forward.log
+python -m pytest tests/test_sampler_gpu.py tests/test_coslam_mapper.py -x -q -m gpu 2>&1 | tail -3
+python bench.py --steps 20 --warmup 5 --no-side-configs --no-torch-gpu-baseline --no-cpu-baseline --sweep-rays 0 > gpurun_out/r3u_bench.json 2> gpurun_out/r3u_bench.err; tail -c 300 gpurun_out/r3u_bench.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r3u_bench.json').read().strip().splitlines()[-1]); print(d['value'], d['e2e']['value']); print(d.get('e2e_mapper')); print(d['roofline']['hash_gather'])"
