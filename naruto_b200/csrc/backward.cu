@@ -30,12 +30,22 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const __grid_constan
   const float g_rgbl = loss_grad[NRT_LOSS_RGB], g_depl = loss_grad[NRT_LOSS_DEPTH], g_sdfl = loss_grad[NRT_LOSS_SDF];
   const float g_fsl = loss_grad[NRT_LOSS_FS], g_uncl = loss_grad[NRT_LOSS_UNCERT];
   const float tr = P.sc_trunc;
+  const bool have_out = rend.rgb && rend.depth && rend.uncert;
 
   for (int64_t ray = (int64_t)blockIdx.x * wpb + warp; ray < n_rays; ray += (int64_t)gridDim.x * wpb) {
     for (int s = lane; s < S; s += 32) z[s] = rend.z_vals[ray * S + s];
     for (int i = lane; i < S * 5; i += 32) raw[i] = rend.raw[ray * S * 5 + i];
     __syncwarp();
-    RayOut ro = warp_composite(P, S, raw, z, wbuf, lane);
+    RayOut ro;
+    if (have_out) {
+      // the forward left the ray's composited colour / depth / uncertainty in its output buffers: only the weights are re-formed
+      warp_weights(P, S, raw, z, wbuf, lane, ro.z_cut, ro.wsum);
+      ro.rgb[0] = __ldg(rend.rgb + ray * 3), ro.rgb[1] = __ldg(rend.rgb + ray * 3 + 1), ro.rgb[2] = __ldg(rend.rgb + ray * 3 + 2);
+      ro.depth = __ldg(rend.depth + ray);
+      ro.uncert = __ldg(rend.uncert + ray);
+    } else {
+      ro = warp_composite(P, S, raw, z, wbuf, lane);
+    }
     __syncwarp();
     const float td = __ldg(target_d + ray);
     const bool valid = td > 0.0f && td < P.depth_trunc;

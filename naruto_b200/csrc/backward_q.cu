@@ -752,9 +752,15 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
                                                             unsigned int* __restrict__ counter) {
   __shared__ float s_sum[8][128];
   __shared__ float Ms[32 * 33];
+  __shared__ float s_w2g[NRT_GEO * 32];      // W2[1+g][m] and W3[j][48+g]: the contraction's weight operands, fetched by every M block
+  __shared__ float s_w3g[32 * NRT_GEO];      // at entry so that the last one does not start two more trips to L2 behind the counter
   __shared__ unsigned int s_last;
   const int t = threadIdx.x, grp = t >> 7, el = t & 127;
   const bool m_block = blockIdx.x >= WG_DIRECT_BLOCKS;
+  if (m_block) {
+    if (t < NRT_GEO * 32) s_w2g[t] = __ldg(prm.w2 + 32 + t);                                   // rows 1..15 of W2, contiguous
+    else if (t >= 512 && t < 512 + 32 * NRT_GEO) s_w3g[t - 512] = __ldg(prm.w3 + ((t - 512) / NRT_GEO) * 63 + NRT_OB + (t - 512) % NRT_GEO);
+  }
   int e, src;
   float* dst = nullptr;
   if (m_block) {
@@ -789,7 +795,7 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
       const int j = t / NRT_GEO, g = t % NRT_GEO;
       float acc = 0.f;
 #pragma unroll 8
-      for (int m = 0; m < 32; ++m) acc = fmaf(Ms[j * 33 + m], __ldg(prm.w2 + (1 + g) * 32 + m), acc);
+      for (int m = 0; m < 32; ++m) acc = fmaf(Ms[j * 33 + m], s_w2g[g * 32 + m], acc);
       grads.w3[j * 63 + NRT_OB + g] += acc;
     }
   } else if (t >= 512 && t < 992) {
@@ -798,7 +804,7 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const float* __restr
       const int g = u >> 5, m = u & 31;
       float acc = 0.f;
 #pragma unroll 8
-      for (int j = 0; j < 32; ++j) acc = fmaf(__ldg(prm.w3 + j * 63 + NRT_OB + g), Ms[j * 33 + m], acc);
+      for (int j = 0; j < 32; ++j) acc = fmaf(s_w3g[j * NRT_GEO + g], Ms[j * 33 + m], acc);
       grads.w2[(1 + g) * 32 + m] += acc;
     }
   }

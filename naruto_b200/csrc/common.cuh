@@ -626,6 +626,45 @@ __device__ __forceinline__ RayOut warp_composite(const DevPlan& P, const int S, 
   return r;
 }
 
+// The weight half of warp_composite() alone -- first sign change, truncation cut, normalised bell weights -> w_out[S] -- for a caller
+// that already holds the ray's composited outputs (the backward pass reads them from the forward's output buffers instead of
+// integrating colour / depth / uncertainty a second time).  Same expressions, same bits as warp_composite().
+__device__ __forceinline__ void warp_weights(const DevPlan& P, const int S, const float* __restrict__ raw, const float* __restrict__ z,
+                                             float* __restrict__ w_out, int lane, float& z_cut, float& wsum) {
+  constexpr int NP = NRT_SMAX / 32;
+  int first = 0x7fffffff;
+  for (int s = lane; s < S - 1; s += 32) {
+    if (raw[(s + 1) * 5 + 3] * raw[s * 5 + 3] < 0.0f) {
+      first = s;
+      break;
+    }
+  }
+  first = warp_min_i(first);
+  if (first == 0x7fffffff) first = 0;
+  z_cut = __fadd_rn(z[first], P.sc_trunc);
+  float bw[NP];
+  float ws = 0.f;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    if (p * 32 >= S) break;
+    const int s = p * 32 + lane;
+    bw[p] = 0.f;
+    if (s < S) {
+      if (z[s] < z_cut) bw[p] = bell_weight(raw[s * 5 + 3], P.trunc);
+      ws += bw[p];
+    }
+  }
+  ws = warp_sum(ws);
+  wsum = ws;
+  const float denom = ws + 1e-8f;
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    if (p * 32 >= S) break;
+    const int s = p * 32 + lane;
+    if (s < S) w_out[s] = z[s] < z_cut ? __fdiv_rn(bw[p], denom) : 0.f;
+  }
+}
+
 // Saved hash features (NrtRenderOut::feat) are stored tile-major: point p, chunk c (4 floats = the two features of two levels)
 // lives at float4 index ((p / 128) * 8 + c) * 128 + p % 128, i.e. [tile of 128 points][8 chunks][128 points][4 floats].  Both the
 // writers (gather threads: one chunk of 32 consecutive points) and the readers (backward thread pairs: chunks of 32 consecutive
