@@ -1,11 +1,12 @@
 """Fused mapping iteration: the body of CoSLAMNaruto.global_BA's loop (src/slam/coslam/coslam.py:364-399) --
 model.forward, get_loss_from_ret(smooth=True), loss.backward(), map_optimizer.step()/zero_grad() and the every-5th
-uncert_optim.step()/zero_grad() -- as a fixed sequence of launches into libnaruto_b200.so, captured once into a
-CUDA graph and replayed.
+uncert_optim.step()/zero_grad() -- as a fixed sequence of 8 launches into libnaruto_b200.so (the smoothness pair on a forked
+branch), captured once into a CUDA graph and replayed.
 
 Data parallel: each rank renders its own shard of the ray batch; the loss statistics (11 doubles) are
-all-reduced before the backward pass because every loss is a ratio of global sums, and the flat gradient buffer
-[grid | w1 | w2 | w3 | w4 | uncert] is all-reduced (NCCL over NVLink) before an identical Adam step on every rank.
+exchanged before the backward pass because every loss is a ratio of global sums, and the flat gradient buffer
+[grid | w1 | w2 | w3 | w4 | uncert] is reduce-scattered, stepped and all-gathered by ONE kernel over NVLink peer memory
+(csrc/peer.cu; NCCL all-reduces + the same Adam launch where symmetric memory is unavailable or NRT_DP_IMPL=nccl).
 """
 import os
 
@@ -222,7 +223,7 @@ class MappingStep:
         self.seed = self.base_seed + 7919 * self.rank
         self._graphs = {}
         # The ray-independent smoothness term runs on a forked branch of the iteration, joined before the optimiser step
-        # (NRT_SMOOTH_FORK: 0 in line, 1 forked after the iteration's first launch, 2 forked after the render forward), held
+        # (NRT_SMOOTH_FORK: 0 in line, 1 forked after the iteration's first launch, 2 forked after the render forward = default), held
         # back by NRT_SMOOTH_STAGGER one-block launches so that the ray path's next kernel (composite_bwd) is resident first
         # and the lattice kernels fill in around it.  Measured on B200 (profiles/r02d_smooth_branch.log), us per iteration at
         # 4096 rays x 128 samples / 2048 x 43: in line 449 / 213; fork 1 426 / 203; fork 2 433 / 187; fork 2 + stagger 2
@@ -267,11 +268,8 @@ class MappingStep:
                 zeroing = True
             if smooth and self.smooth_fork == 1 and not zeroing:
                 n += self._smooth_branch(); forked = True
-            ev = torch.cuda.current_stream().record_event() if smooth and self.smooth_fork == 3 else None
             p.render_fwd_stats(self.P, self.rays_o, self.rays_d, self.target_rgb, self.target_d, self.out, self.stats, u=None,
                                seed=self.seed, seed_step=self.map_step, losses=fused_losses); n += 1
-            if ev is not None:                              # forked before the forward, launched after it
-                n += self._smooth_branch(ev); forked = True
         if zeroing:
             torch.cuda.current_stream().wait_stream(self._zero_branch)
         self._mark('forward')
@@ -322,17 +320,14 @@ class MappingStep:
             self.stamp_names.append(name)
         L.check(self.plan.lib.nrt_debug_stamp(self.stamps.data_ptr() + 8 * k, torch.cuda.current_stream().cuda_stream))
 
-    def _smooth_branch(self, after=None):
+    def _smooth_branch(self):
         """Launch the smoothness term on a second stream forked off the current one (inside a capture this becomes a parallel
         branch of the graph): it reads the parameters and rand6 and adds into the table gradient with reductions, so it only
         has to be ordered before the optimiser step."""
         p = self.plan
         if self._branch is None:
             self._branch = torch.cuda.Stream(device=self.dev)
-        if after is None:
-            self._branch.wait_stream(torch.cuda.current_stream())
-        else:
-            self._branch.wait_event(after)
+        self._branch.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._branch):
             for _ in range(self.smooth_stagger):
                 self.smooth_loss.zero_()
