@@ -287,11 +287,13 @@ typedef struct NrtAdamGroup {
 } NrtAdamGroup;
 
 /* all-reduce of the loss statistics + nrt_loss_finalize in one launch: stats (dev, this rank's sums from
- * nrt_render_fwd_stats) is overwritten with the global sums, losses as nrt_loss_finalize.  xchg: dev u32 exchange counter of
+ * nrt_render_fwd_stats) is overwritten with the global sums, losses as nrt_loss_finalize.  The statistics cross NVLink as
+ * 8-byte words that carry the exchange number next to 32 data bits (no fence, no separate flag).  xchg: dev u32 exchange counter of
  * this rank (zero-filled once; advanced here, read by nrt_adam_step_peers). */
 int nrt_stats_exchange(const NrtPeerTable* peers, double* stats, uint32_t* xchg, float* losses, void* stream);
 /* reduce-scatter + Adam + all-gather in one launch: every rank reduces and steps its 1/world slice of each enabled group
- * (gradients summed over the ranks in rank order, then cleared on every rank), with its local moments exp_avg / exp_avg_sq
+ * (gradients summed over the ranks in rank order -- or inside the NVSwitch when peers->bucket_mc is set -- then cleared on every
+ * rank unless the group's keep_grad is set), with its local moments exp_avg / exp_avg_sq
  * (dev fp32 [total]; only the rank's own slices are maintained), and stores the updated parameters into every rank's theta.
  * smooth_slot: index of the smoothness-loss slot in bucket (its sum over ranks -> smooth_total, dev fp32 [1], may be NULL).
  * done_counter: dev u32 scratch, zero-filled once.  Returns after every rank's stores are visible everywhere. */
